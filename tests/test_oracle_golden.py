@@ -1,0 +1,129 @@
+"""Pins the oracle restatement against golden vectors generated from the LIVE reference
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+from conftest import state_dict_from
+from oracle import heatmaps as ohm
+from oracle import loss as oloss
+from oracle import steps as osteps
+from oracle import tiling as otiling
+from oracle import unet as ounet
+
+TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def _cos(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return float(a @ b / (a.norm() * b.norm() + 1e-30))
+
+
+def test_unet3d_forward_losses_grads(golden):
+    g = golden("unet3d_small")
+    sd = osteps.leaf_state_dict(state_dict_from(g))
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    logits = ounet.unet3d_forward(sd, x, f_maps=[8, 16, 32])
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits"], **TOL)
+    dice = oloss.dice_loss(logits, y, weight=torch.tensor([0.05, 1.0]))
+    ce = oloss.weighted_cross_entropy(logits, y, torch.tensor([0.3, 0.7]))
+    np.testing.assert_allclose(dice.item(), g["dice"], rtol=1e-6)
+    np.testing.assert_allclose(ce.item(), g["ce"], rtol=1e-6)
+    np.testing.assert_allclose(oloss.dice_metric(logits, y).detach().numpy(), g["dice_metric"], rtol=1e-5)
+    grads = osteps.grads_of(dice, sd)
+    for k, v in grads.items():
+        ref = torch.from_numpy(g["grad." + k])
+        assert _cos(v, ref) > 0.99999, k
+        np.testing.assert_allclose(v.numpy(), ref.numpy(), rtol=2e-3, atol=1e-7, err_msg=k)
+
+
+def test_unet3d_odd_size_and_testing_mode(golden):
+    g = golden("unet3d_small")
+    sd = state_dict_from(g)
+    out = ounet.unet3d_forward(sd, torch.from_numpy(g["x_odd"]), f_maps=[8, 16, 32])
+    np.testing.assert_allclose(out.numpy(), g["logits_odd"], **TOL)
+    probs = ounet.unet3d_forward(sd, torch.from_numpy(g["x"]), f_maps=[8, 16, 32], testing=True)
+    np.testing.assert_allclose(probs.numpy(), g["probs"], **TOL)
+
+
+def test_unet3d_layer_orders(golden):
+    g = golden("unet3d_orders")
+    for order in ("crg", "cl", "gce"):
+        sd = state_dict_from(g, f"{order}.sd.")
+        out = ounet.unet3d_forward(sd, torch.from_numpy(g[f"{order}.x"]), f_maps=[8, 16], layer_order=order)
+        np.testing.assert_allclose(out.numpy(), g[f"{order}.logits"], **TOL)
+
+
+def test_residual_landmark_step(golden):
+    g = golden("residual_small")
+    sd = osteps.leaf_state_dict(state_dict_from(g))
+    label = np.concatenate([g["heatmaps"], g["label"][:, None].astype(np.float32)], axis=1)
+    batch = {"data": torch.from_numpy(g["x"]), "label": torch.from_numpy(label)}
+    total, cls, reg, outputs = osteps.landmark_step("residual", sd, batch, loss_regression_weight=g["reg_w"].tolist(),
+                                                    f_maps=[8, 16, 32])
+    np.testing.assert_allclose(outputs.detach().numpy(), g["outputs"], **TOL)
+    np.testing.assert_allclose(cls.item(), g["class_loss"], rtol=1e-6)
+    np.testing.assert_allclose(reg.item(), g["regression_loss"], rtol=1e-5)
+    np.testing.assert_allclose(total.item(), g["loss"], rtol=1e-5)
+    for k, v in osteps.grads_of(total, sd).items():
+        assert _cos(v, torch.from_numpy(g["grad." + k])) > 0.99999, k
+
+
+def test_state_dict_factories_match_reference_keys(golden):
+    g = golden("unet3d_small")
+    ref = {k: v.shape for k, v in state_dict_from(g).items()}
+    mine = {k: tuple(v.shape) for k, v in ounet.make_unet3d_state_dict(1, 2, [8, 16, 32]).items()}
+    assert mine == {k: tuple(s) for k, s in ref.items()}
+    g = golden("residual_small")
+    ref = {k: tuple(v.shape) for k, v in state_dict_from(g).items()}
+    mine = {k: tuple(v.shape) for k, v in ounet.make_residual_unet3d_state_dict(1, 4, [8, 16, 32]).items()}
+    assert mine == ref
+
+
+def test_tiling_matches_reference_generator(golden):
+    g = golden("tiling")
+    for tag in "abc":
+        img, (p, o) = g[f"{tag}.img"], g[f"{tag}.patch"]
+        pos, sums = [], []
+        for patch, idx, _ in otiling.grid_patches(img, [p] * 3, [o] * 3, mode="constant"):
+            pos.append(idx)
+            sums.append(patch.astype(np.float64).sum())
+        np.testing.assert_array_equal(np.array(pos), g[f"{tag}.pos"])
+        np.testing.assert_allclose(np.array(sums), g[f"{tag}.sums"], rtol=1e-12)
+        # identity model: tile + centre-crop + stitch reproduces the input
+        res = np.zeros_like(img)
+        for patch, idx, _ in otiling.grid_patches(img, [p] * 3, [o] * 3, mode="constant"):
+            otiling.stitch_patch(res, patch, idx, [o] * 3)
+        np.testing.assert_array_equal(res, img)
+
+
+def test_semantics_kats(golden):
+    import torch.nn.functional as F
+    g = golden("semantics")
+    src = np.minimum(np.floor(np.arange(25) * 12 / 25), 11)
+    np.testing.assert_array_equal(g["nearest_12_to_25"], src)
+    assert g["pool_equal_idx"].item() == 0
+    assert g["pool_nan_idx"].item() == 5 and np.isnan(g["pool_nan_val"]).all()
+    assert g["argmax_tie"].item() == 1
+    ce = oloss.weighted_cross_entropy(torch.from_numpy(g["ce_logits"]), torch.from_numpy(g["ce_label"]),
+                                      torch.from_numpy(g["ce_w"]))
+    np.testing.assert_allclose(ce.item(), g["ce_value"], rtol=1e-6)
+
+
+def test_predict_epilogue_truncation_and_first_max():
+    logits = np.zeros((1, 3, 1, 1, 4), dtype=np.float32)
+    logits[0, 0, 0, 0] = [-3.0, 17.9, 255.5, 300.0]          # heatmap channel
+    logits[0, 1, 0, 0] = [1.0, 2.0, 0.0, 5.0]
+    logits[0, 2, 0, 0] = [1.0, 1.0, 3.0, 5.0]
+    out = otiling.predict_epilogue(logits, 1)
+    np.testing.assert_array_equal(out[0, 0, 0, 0], [0, 17, 255, 255])
+    np.testing.assert_array_equal(out[0, 1, 0, 0], [0, 0, 1, 0])
+
+
+def test_heatmap_oracle_roundtrip():
+    pts = np.array([[[3.0, 4.0, 5.0], [10.0, 2.0, 7.0]]], dtype=np.float32)
+    hm = ohm.render_heatmaps(pts, [2.0, 3.0], (12, 12, 12))
+    assert hm.dtype == np.uint8 and hm.max() == 255
+    idx = ohm.argmax_landmarks(torch.from_numpy(hm))
+    np.testing.assert_array_equal(idx.numpy()[0], pts[0].astype(np.int64))
+    soft = ohm.soft_argmax_landmarks(torch.from_numpy(hm).float(), beta=0.2)
+    assert np.abs(soft.numpy()[0, 0] - pts[0, 0]).max() < 0.5
