@@ -1,0 +1,380 @@
+/*
+ * mednet_b200.h -- C ABI of the B200-native (sm_100a) UNet3D hot path for torch-mednet.
+ *
+ * The reference (tobiashepp/torch-mednet) has no FFI: every FLOP of its hot path runs inside
+ * third-party PyTorch/ATen ops (requirements.txt:5).  Each entry point below therefore replaces one
+ * ATen call site of the reference; the call site is cited per function as `ref: file:line`
+ * (paths relative to the reference root, midasmednet/ = mm/).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator on the Python
+ *     side).  Launchers never allocate, free or synchronise; they enqueue on `stream` and return.
+ *   - Activations are NDHWC ("channels-last-3d"), contiguous, dtype MEDNET_F32 or MEDNET_BF16.
+ *     Logits / losses are NCDHW fp32 at the module boundary (the layout the reference returns).
+ *   - Return value: 0 = success; negative = MEDNET_E* (unsupported shape / dtype / alignment -- the
+ *     Python side raises, there is no fallback); positive = cudaError_t of the failed launch.
+ *   - Re-entrant and stream ordered; the only global state is an immutable lazily built attribute /
+ *     tensor-map encoder cache behind a mutex.
+ *   - `workspace` is scratch of at least mednet_<op>_workspace_bytes(p) bytes, 256-byte aligned.
+ */
+#ifndef MEDNET_B200_H
+#define MEDNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mednet_stream_t;
+
+#define MEDNET_ABI_VERSION 1
+
+/* dtypes */
+#define MEDNET_F32  0
+#define MEDNET_BF16 1
+#define MEDNET_U8   2
+#define MEDNET_I64  3
+
+/* activations (ref: mm/unet/components.py:35-40) */
+#define MEDNET_ACT_NONE  0
+#define MEDNET_ACT_RELU  1
+#define MEDNET_ACT_LEAKY 2   /* negative slope in act_param (reference uses 0.1) */
+#define MEDNET_ACT_ELU   3   /* alpha = 1 */
+
+/* convolution implementations */
+#define MEDNET_IMPL_AUTO    0
+#define MEDNET_IMPL_SIMT    1   /* CUDA-core fp32-accumulate implicit GEMM (fp32 validation mode, odd shapes) */
+#define MEDNET_IMPL_TCGEN05 2   /* tcgen05/TMEM tensor-core implicit GEMM with TMA halo tiles (bf16) */
+
+/* packed-weight layouts produced by mednet_conv3d_pack_weights */
+#define MEDNET_WPACK_SIMT_FPROP    0   /* [Cout][27][Cin]            */
+#define MEDNET_WPACK_SIMT_DGRAD    1   /* [Cin][27 flipped][Cout]     */
+#define MEDNET_WPACK_TC_FPROP      2   /* [27][Cout][Cin]            */
+#define MEDNET_WPACK_TC_DGRAD      3   /* [27 flipped][Cin][Cout]     */
+
+/* gather modes of the generic implicit GEMM */
+#define MEDNET_GATHER_CONV3   0   /* 3x3x3, stride 1, pad 1               */
+#define MEDNET_GATHER_CONVT_F 1   /* transposed k3 s2 p1 op1, output->input */
+#define MEDNET_GATHER_CONVT_B 2   /* transposed k3 s2 p1 op1, input->output */
+
+/* error codes */
+#define MEDNET_OK            0
+#define MEDNET_EINVAL       (-1)
+#define MEDNET_EUNSUPPORTED (-2)
+#define MEDNET_EALIGN       (-3)
+#define MEDNET_EWORKSPACE   (-4)
+#define MEDNET_ENODRIVER    (-5)
+
+int         mednet_abi_version(void);
+const char* mednet_error_string(int code);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMEM present) */
+int         mednet_device_has_tcgen05(void);
+int         mednet_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / dtype conversion at the module boundary.
+ * ref: the reference keeps NCDHW fp32 everywhere (mm/segmentation.py:59 `batch['data'].float()`).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* src; void* dst;
+  int64_t N, C, S;            /* S = D*H*W */
+  int32_t src_dtype, dst_dtype;
+  int32_t to_channels_last;   /* 1: NCDHW -> NDHWC, 0: NDHWC -> NCDHW */
+} mednet_layout_params;
+int mednet_layout_convert(const mednet_layout_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3x3x3 convolution, stride 1, zero padding 1 (also hosts ConvTranspose3d through `gather`).
+ * ref: mm/unet/components.py:8-9 (nn.Conv3d via create_conv :41-44); transposed: :259-264.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  w_oidhw;   /* fp32 PyTorch layout: conv (Cout,Cin,3,3,3); transposed conv (Cin,Cout,3,3,3) */
+  void*        w_packed;
+  int32_t Cin, Cout;      /* of the forward op */
+  int32_t dtype;          /* dtype of w_packed */
+  int32_t layout;         /* MEDNET_WPACK_* */
+  int32_t transposed;     /* 1: w_oidhw is a ConvTranspose3d weight */
+} mednet_wpack_params;
+int mednet_conv3d_pack_weights(const mednet_wpack_params* p, mednet_stream_t stream);
+
+typedef struct {
+  const void*  x;         /* [N, Di,Hi,Wi, K]  rows gathered from here                     */
+  const void*  w;         /* packed weights, see MEDNET_WPACK_* ([Nout][27][K] or [27][Nout][K]) */
+  const float* bias;      /* [Nout] or NULL                                                 */
+  const void*  addend;    /* optional tensor of y's shape added before the activation (skip sum, ref :284) */
+  void*        y;         /* [N, Do,Ho,Wo, Nout]                                            */
+  int32_t N, Di, Hi, Wi, Do, Ho, Wo;
+  int32_t K, Nout;        /* reduction channels / output channels of THIS gemm              */
+  int32_t dtype, act; float act_param;
+  int32_t gather;         /* MEDNET_GATHER_*                                                */
+  int32_t impl;           /* MEDNET_IMPL_*                                                  */
+} mednet_conv3d_params;
+size_t mednet_conv3d_workspace_bytes(const mednet_conv3d_params* p);
+/* Resolves p->impl (MEDNET_IMPL_AUTO included) to the implementation that will run, so the caller can
+ * pack the weights in the matching layout; negative = MEDNET_E*. */
+int    mednet_conv3d_select_impl(const mednet_conv3d_params* p);
+/* y = act(gather-conv(x, w) + bias + addend).  fprop and dgrad are the same launcher with different
+ * packed weights (dgrad of a stride-1 conv is the conv of dY with the flipped, transposed filter). */
+int mednet_conv3d_fprop(const mednet_conv3d_params* p, void* workspace, size_t workspace_bytes,
+                        mednet_stream_t stream);
+
+typedef struct {
+  const void* a;          /* [N, Da,Ha,Wa, Ca] "row" operand (conv: dY; transposed conv: x)          */
+  const void* b;          /* [N, Db,Hb,Wb, Cb] gathered operand (conv: x; transposed conv: dY)       */
+  float*      dw;         /* fp32 gradient in PyTorch layout (Ca,Cb,3,3,3)                           */
+  float*      dbias;      /* optional bias gradient = column sums of the output-gradient operand
+                             (a, [Ca], for GATHER_CONV3; b, [Cb], for GATHER_CONVT_B) or NULL        */
+  int32_t N, Da, Ha, Wa, Db, Hb, Wb, Ca, Cb;
+  int32_t dtype, gather, impl;
+  int32_t accumulate;     /* 1: dw += result (gradient accumulation), 0: overwrite                   */
+} mednet_wgrad_params;
+size_t mednet_conv3d_wgrad_workspace_bytes(const mednet_wgrad_params* p);
+int    mednet_conv3d_wgrad_select_impl(const mednet_wgrad_params* p);
+int    mednet_conv3d_wgrad(const mednet_wgrad_params* p, void* workspace, size_t workspace_bytes,
+                           mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Final 1x1x1 convolution with bias: NDHWC activations -> NCDHW fp32 logits.
+ * ref: mm/unet/model.py:77,102 (UNet3D) and :179,207 (ResidualUNet3D).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  x;         /* [N*S, Cin] NDHWC                         */
+  const float* w;         /* [Cout, Cin] fp32                         */
+  const float* bias;      /* [Cout]                                   */
+  float*       y;         /* [N, Cout, S] fp32                        */
+  int64_t N, S; int32_t Cin, Cout, dtype;
+} mednet_conv1_params;
+int mednet_conv1x1_fwd(const mednet_conv1_params* p, mednet_stream_t stream);
+typedef struct {
+  const void*  x; const float* w; const float* dy;   /* dy [N, Cout, S] fp32 */
+  void*        dx;        /* [N*S, Cin] NDHWC (dtype)                 */
+  float*       dw;        /* [Cout, Cin]                              */
+  float*       db;        /* [Cout]                                   */
+  int64_t N, S; int32_t Cin, Cout, dtype; int32_t accumulate;
+} mednet_conv1_bwd_params;
+size_t mednet_conv1x1_bwd_workspace_bytes(const mednet_conv1_bwd_params* p);
+int    mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* workspace, size_t workspace_bytes,
+                          mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional residual add + activation), eps 1e-5, biased variance.
+ * ref: mm/unet/components.py:57 (nn.GroupNorm), :36-40 (activation after it), :177-178 (residual).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  x;         /* [N, S, C]                                                        */
+  const float* gamma; const float* beta;      /* [C]                                          */
+  const void*  residual;  /* optional [N,S,C] added before the activation, or NULL            */
+  void*        y;         /* [N, S, C]                                                        */
+  float*       mean; float* rstd;             /* [N, G] outputs (saved for backward)          */
+  int64_t N, S; int32_t C, G, dtype, act; float act_param, eps;
+} mednet_gn_fwd_params;
+size_t mednet_groupnorm_fwd_workspace_bytes(const mednet_gn_fwd_params* p);
+int    mednet_groupnorm_fwd(const mednet_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
+                            mednet_stream_t stream);
+typedef struct {
+  const void*  x; const void* y;              /* y = saved forward output (needed iff act != NONE) */
+  const void*  dy;
+  const float* gamma; const float* mean; const float* rstd;
+  void*        dx;        /* [N,S,C]                                                          */
+  void*        dresidual; /* optional [N,S,C]: gradient wrt the residual input, or NULL       */
+  float*       dgamma; float* dbeta;          /* [C]                                          */
+  int64_t N, S; int32_t C, G, dtype, act; float act_param; int32_t accumulate;
+} mednet_gn_bwd_params;
+size_t mednet_groupnorm_bwd_workspace_bytes(const mednet_gn_bwd_params* p);
+int    mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
+                            mednet_stream_t stream);
+
+/* Stand-alone activation backward from the saved OUTPUT (conv epilogue activations):
+ * dx = dy * act'(y).  ref: ReLU/LeakyReLU/ELU in-place modules, mm/unet/components.py:35-40. */
+typedef struct {
+  const void* y; const void* dy; void* dx; int64_t numel; int32_t dtype, act; float act_param;
+} mednet_act_bwd_params;
+int mednet_act_bwd(const mednet_act_bwd_params* p, mednet_stream_t stream);
+/* Stand-alone activation forward (orders such as 'crg' where the activation is not fused). */
+typedef struct {
+  const void* x; void* y; int64_t numel; int32_t dtype, act; float act_param;
+} mednet_act_fwd_params;
+int mednet_act_fwd(const mednet_act_fwd_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MaxPool3d(kernel 2, stride 2, floor mode) with argmax.
+ * ref: mm/unet/components.py:210 (nn.MaxPool3d), applied at :224.
+ * Tie rule: first maximum in (d,h,w) scan order; NaN wins (ATen semantics, golden semantics.npz).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;          /* [N, D, H, W, C]                                                  */
+  void*       y;          /* [N, D/2, H/2, W/2, C]                                            */
+  uint8_t*    idx;        /* [N, D/2, H/2, W/2, C] window-local argmax code dz*4+dy*2+dx      */
+  int32_t N, D, H, W, C, dtype;
+} mednet_pool_params;
+int mednet_maxpool3d_fwd(const mednet_pool_params* p, mednet_stream_t stream);
+typedef struct {
+  const void* dy; const uint8_t* idx; void* dx; int32_t N, D, H, W, C, dtype;
+} mednet_pool_bwd_params;
+int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stream_t stream);
+/* Expand the 3-bit codes to ATen's int64 flat D*H*W indices, NCDHW order (parity checks only). */
+int mednet_maxpool3d_indices_i64(const uint8_t* idx, int64_t* out, int32_t N, int32_t D, int32_t H,
+                                 int32_t W, int32_t C, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Nearest-neighbour upsampling to the skip tensor's size fused with the channel concat
+ * (encoder features first).  ref: mm/unet/components.py:277-280 (F.interpolate + torch.cat).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* skip;       /* [N, D, H, W, Cs]                                                 */
+  const void* low;        /* [N, d, h, w, Cl]                                                 */
+  void*       out;        /* [N, D, H, W, Cs+Cl]                                              */
+  int32_t N, D, H, W, d, h, w, Cs, Cl, dtype;
+} mednet_upcat_params;
+int mednet_upsample_concat_fwd(const mednet_upcat_params* p, mednet_stream_t stream);
+typedef struct {
+  const void* dout; void* dskip; void* dlow; int32_t N, D, H, W, d, h, w, Cs, Cl, dtype;
+} mednet_upcat_bwd_params;
+int mednet_upsample_concat_bwd(const mednet_upcat_bwd_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses on NCDHW logits.  `logits` may be a channel slice of a wider tensor: element (n,c,s) lives
+ * at logits[n*batch_stride + c*S + s].  Labels are MEDNET_I64 or MEDNET_U8 class maps [N,S].
+ * All reductions are two-stage and deterministic.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  logits; const void* labels; const float* weight;   /* weight [C] or NULL */
+  float*       sums;      /* [3][C]: intersect (unweighted), sum p, count -- saved for backward */
+  float*       dice;      /* [C] per-channel dice (weighted on the intersect, ref mm/unet/loss.py:44-45) */
+  float*       loss;      /* scalar: mean_c(1 - dice_c)                                          */
+  int64_t N, S, batch_stride; int32_t C, logits_dtype, label_dtype, sigmoid; float epsilon;
+} mednet_dice_params;
+size_t mednet_dice_workspace_bytes(const mednet_dice_params* p);
+/* ref: mm/unet/loss.py:114-130 (DiceLoss.forward) with :10-48, :58-88; dice_metric :51-55. */
+int    mednet_dice_fwd(const mednet_dice_params* p, void* workspace, size_t workspace_bytes,
+                       mednet_stream_t stream);
+typedef struct {
+  const void*  logits; const void* labels; const float* weight; const float* sums;
+  const float* grad_out;  /* device scalar upstream gradient                                     */
+  void*        dlogits;   /* same addressing as logits (batch_stride_out), dtype dlogits_dtype   */
+  int64_t N, S, batch_stride, batch_stride_out; int32_t C, logits_dtype, label_dtype, dlogits_dtype, sigmoid;
+  float epsilon;
+} mednet_dice_bwd_params;
+int    mednet_dice_bwd(const mednet_dice_bwd_params* p, mednet_stream_t stream);
+
+typedef struct {
+  const void*  logits; const void* labels; const float* weight;
+  float*       sums;      /* [2]: sum w[y]*nll, sum w[y]  (saved)                                */
+  float*       loss;      /* scalar                                                               */
+  int64_t N, S, batch_stride; int32_t C, logits_dtype, label_dtype;
+} mednet_ce_params;
+size_t mednet_ce_workspace_bytes(const mednet_ce_params* p);
+/* ref: mm/segmentation.py:49, mm/landmarks.py:49 (nn.CrossEntropyLoss(weight), weighted mean). */
+int    mednet_ce_fwd(const mednet_ce_params* p, void* workspace, size_t workspace_bytes, mednet_stream_t stream);
+typedef struct {
+  const void*  logits; const void* labels; const float* weight; const float* sums; const float* grad_out;
+  void*        dlogits;
+  int64_t N, S, batch_stride, batch_stride_out; int32_t C, logits_dtype, label_dtype, dlogits_dtype;
+} mednet_ce_bwd_params;
+int    mednet_ce_bwd(const mednet_ce_bwd_params* p, mednet_stream_t stream);
+
+typedef struct {
+  const void*  pred;      /* channel slice, element (n,c,s) at pred[n*batch_stride + c*S + s]    */
+  const void*  target;    /* [N, L, S] MEDNET_U8 or MEDNET_F32 heatmaps (0..255)                 */
+  const float* weight;    /* [L] per-channel weights (ref mm/landmarks.py:128-132)                */
+  float*       per_channel; /* [L] mean error per channel                                         */
+  float*       loss;      /* scalar sum_c w_c * mean_c                                            */
+  int64_t N, S, batch_stride; int32_t L, pred_dtype, target_dtype, l1;
+} mednet_hmloss_params;
+size_t mednet_heatmap_loss_workspace_bytes(const mednet_hmloss_params* p);
+/* ref: mm/landmarks.py:53-55,125-134 (MSELoss / L1Loss per channel, python loop). */
+int    mednet_heatmap_loss_fwd(const mednet_hmloss_params* p, void* workspace, size_t workspace_bytes,
+                               mednet_stream_t stream);
+typedef struct {
+  const void*  pred; const void* target; const float* weight; const float* grad_out;
+  void*        dpred;
+  int64_t N, S, batch_stride, batch_stride_out; int32_t L, pred_dtype, target_dtype, dpred_dtype, l1;
+} mednet_hmloss_bwd_params;
+int    mednet_heatmap_loss_bwd(const mednet_hmloss_bwd_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inference epilogue: uint8 heatmaps (clip to [0,255], truncate) and uint8 argmax class map written
+ * directly from logits.  ref: examples/predict.py:88-94.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* logits;     /* [N, L+K, S] */
+  uint8_t*    out;        /* [N, L+1, S] */
+  int64_t N, S; int32_t L, K, logits_dtype;
+} mednet_predict_params;
+int mednet_predict_epilogue(const mednet_predict_params* p, mednet_stream_t stream);
+
+/* Test-time activation over the channel axis of NCDHW fp32 logits: softmax (sigmoid = 0) or sigmoid.
+ * ref: mm/unet/model.py:79-82,107-108. */
+int mednet_final_activation(const float* logits, float* out, int64_t N, int64_t S, int32_t C, int32_t sigmoid,
+                            mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Adam on a flat fp32 parameter bucket (PyTorch defaults: no weight decay, no amsgrad).
+ * ref: mm/segmentation.py:119-120, mm/landmarks.py:176-177 (torch.optim.Adam(self.parameters(), lr)).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t numel; float lr, beta1, beta2, eps, grad_scale; int32_t step;
+} mednet_adam_params;
+int mednet_adam_step(const mednet_adam_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Landmark path: Gaussian heatmap rendering and (soft-)argmax extraction.
+ * ABSENT from the reference (heatmaps are read pre-rendered as uint8, mm/dataset.py:261-262);
+ * builder specification in oracle/heatmaps.py.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* points;    /* [N, L, 3] voxel coordinates (d,h,w) */
+  const float* sigmas;    /* [L]                                 */
+  uint8_t*     out;       /* [N, L, D, H, W]                     */
+  int32_t N, L, D, H, W;
+} mednet_hmrender_params;
+int mednet_heatmap_render(const mednet_hmrender_params* p, mednet_stream_t stream);
+typedef struct {
+  const void* heatmaps;   /* [N*L, S] */
+  int64_t*    argmax;     /* [N*L, 3] (d,h,w), first maximal index        */
+  float*      soft;       /* [N*L, 3] soft-argmax with temperature beta, or NULL */
+  int64_t NL; int32_t D, H, W, dtype; float beta;
+} mednet_landmark_params;
+size_t mednet_landmark_workspace_bytes(const mednet_landmark_params* p);
+int    mednet_landmark_extract(const mednet_landmark_params* p, void* workspace, size_t workspace_bytes,
+                               mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sliding-window helpers (tile gather with zero padding / centre-crop scatter), uint8 and float.
+ * ref: mm/dataset.py:349-389 (grid_patch_generator), :444-474 (add_processed_batch).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* volume;     /* [C, X, Y, Z] source volume (NCDHW without N), dtype src_dtype */
+  void*       tiles;      /* [B, P0,P1,P2, C] NDHWC tiles, dtype dst_dtype                  */
+  const int32_t* origins; /* [B, 3] device array of tile origins in PADDED coordinates      */
+  int32_t B, C, X, Y, Z, P0, P1, P2, O0, O1, O2, src_dtype, dst_dtype;
+} mednet_tile_gather_params;
+int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_stream_t stream);
+typedef struct {
+  const uint8_t* tiles;   /* [B, Co, P0*P1*P2] epilogue output                                */
+  uint8_t*       volume;  /* [Co, X, Y, Z]                                                     */
+  const int32_t* origins; /* [B, 3]                                                            */
+  int32_t B, Co, X, Y, Z, P0, P1, P2, O0, O1, O2;
+} mednet_tile_scatter_params;
+int mednet_tile_scatter(const mednet_tile_scatter_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 descriptor-semantics probe (diagnostics; see DESIGN.md "UMMA descriptor experiments").
+ * Runs D = A_window * I for a shifted/strided window of a TMA-written SW128 tile and returns the
+ * gathered rows so the host can tell which descriptor variants address correctly.
+ * ---------------------------------------------------------------------------------------------- */
+/* Selects how the conv kernel addresses its halo tile: dense_halo = 1 -> 10-voxel row pitch, one TMA box
+ * per plane; 0 -> rows padded to a 16-voxel pitch (stride between 8-row groups stays a multiple of the
+ * swizzle atom).  base_offset_mode = 1 -> descriptor base_offset = (start_address >> 7) & 7, 0 -> 0. */
+int mednet_tcgen05_configure(int dense_halo, int base_offset_mode);
+int mednet_tcgen05_probe(const void* a_bf16 /* [rows][64] */, int32_t rows, int32_t row_shift,
+                         int32_t sbo_bytes, int32_t base_offset_mode, float* out /* [128][64] */,
+                         mednet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDNET_B200_H */

@@ -1,0 +1,229 @@
+// Final 1x1x1 convolution with bias: NDHWC activations -> NCDHW fp32 logits, and its backward.
+// ref: midasmednet/unet/model.py:77,102 (UNet3D) and :179,207 (ResidualUNet3D).
+// Memory-bound (Cout = classes + heatmaps is tiny): one pass over the widest activation of the net.
+#include "common.cuh"
+
+namespace mednet {
+
+constexpr int CO_TILE = 8;
+
+// thread per voxel; x row read with 16-byte vectors; weights staged in shared memory
+template <typename T, int V>
+__global__ void conv1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ y, int64_t N, int64_t S, int Cin, int Cout) {
+  extern __shared__ float sw[];  // [Cout][Cin]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int64_t total = N * S;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = r / S, s = r - n * S;
+    const T* xr = x + r * Cin;
+    for (int c0 = 0; c0 < Cout; c0 += CO_TILE) {
+      float acc[CO_TILE];
+#pragma unroll
+      for (int j = 0; j < CO_TILE; ++j) acc[j] = (c0 + j < Cout) ? bias[c0 + j] : 0.f;
+      for (int k = 0; k < Cin; k += V) {
+        float xv[V];
+        load_vec<T, V>(xr + k, xv);
+#pragma unroll
+        for (int j = 0; j < CO_TILE; ++j) {
+          if (c0 + j < Cout) {
+            const float* wr = sw + (c0 + j) * Cin + k;
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[j] = fmaf(xv[i], wr[i], acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CO_TILE; ++j)
+        if (c0 + j < Cout) y[(n * Cout + (c0 + j)) * S + s] = acc[j];
+    }
+  }
+}
+
+// dx[r][ci] = sum_co dy[n][co][s] * w[co][ci]
+template <typename T, int V>
+__global__ void conv1_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
+                                int64_t N, int64_t S, int Cin, int Cout) {
+  extern __shared__ float sw[];  // [Cout][Cin]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int64_t total = N * S;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = r / S, s = r - n * S;
+    T* out = dx + r * Cin;
+    for (int k = 0; k < Cin; k += V) {
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      for (int co = 0; co < Cout; ++co) {
+        const float g = dy[(n * Cout + co) * S + s];
+        const float* wr = sw + co * Cin + k;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(g, wr[i], acc[i]);
+      }
+      store_vec<T, V>(out + k, acc);
+    }
+  }
+}
+
+// partial[b][co][ci] = sum over the block's rows of dy[.,co] * x[.,ci]
+// block = (Cin_t, R): thread (tx,ty) owns input channel tx and rows ty, ty+R, ...
+constexpr int DW_MAX_CO = 16;
+template <typename T>
+__global__ void conv1_dw_partial_kernel(const T* __restrict__ x, const float* __restrict__ dy,
+                                        float* __restrict__ partial, int64_t N, int64_t S, int Cin, int Cout,
+                                        int co0, int64_t rows_per_block) {
+  extern __shared__ float sm[];
+  const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t total = N * S;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > total) r1 = total;
+  const int nco = min(DW_MAX_CO, Cout - co0);
+  float acc[DW_MAX_CO];
+#pragma unroll
+  for (int j = 0; j < DW_MAX_CO; ++j) acc[j] = 0.f;
+  const bool active = ci < Cin;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const int64_t n = r / S, s = r - n * S;
+    const float xv = active ? to_f32<T>(x[r * Cin + ci]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < DW_MAX_CO; ++j) {
+      if (j < nco) {
+        const float g = dy[(n * Cout + co0 + j) * S + s];
+        acc[j] = fmaf(g, xv, acc[j]);
+      }
+    }
+  }
+  // reduce across threadIdx.y
+  const int bx = blockDim.x, R = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int j = 0; j < DW_MAX_CO; ++j) sm[(ty * bx + tx) * DW_MAX_CO + j] = acc[j];
+  __syncthreads();
+  for (int j = ty; j < nco; j += R) {
+    float a = 0.f;
+    for (int t = 0; t < R; ++t) a += sm[(t * bx + tx) * DW_MAX_CO + j];
+    if (active) partial[((int64_t)blockIdx.x * Cout + co0 + j) * Cin + ci] = a;
+  }
+}
+
+// db partial: block b sums dy[:, co, rows of block]
+__global__ void conv1_db_partial_kernel(const float* __restrict__ dy, float* __restrict__ partial_b, int64_t N,
+                                        int64_t S, int Cout, int64_t rows_per_block) {
+  __shared__ float scratch[32];
+  const int64_t total = N * S;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > total) r1 = total;
+  for (int co = 0; co < Cout; ++co) {
+    float a = 0.f;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+      const int64_t n = r / S, s = r - n * S;
+      a += dy[(n * Cout + co) * S + s];
+    }
+    a = block_sum(a, scratch);
+    if (threadIdx.x == 0) partial_b[(int64_t)blockIdx.x * Cout + co] = a;
+  }
+}
+
+__global__ void conv1_dw_final_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b,
+                                      float* __restrict__ dw, float* __restrict__ db, int Cin, int Cout, int nblocks,
+                                      int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = Cout * Cin;
+  if (i < nw) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[(int64_t)b * nw + i];
+    dw[i] = accumulate ? dw[i] + (float)s : (float)s;
+  } else if (i < nw + Cout) {
+    const int co = i - nw;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial_b[(int64_t)b * Cout + co];
+    db[co] = accumulate ? db[co] + (float)s : (float)s;
+  }
+}
+
+struct Conv1Plan {
+  int nblocks, cin_t, cin_tiles, R;
+  int64_t rows_per_block;
+};
+static Conv1Plan conv1_plan(int64_t rows, int Cin) {
+  Conv1Plan pl;
+  pl.cin_t = Cin < 256 ? Cin : 256;
+  pl.cin_tiles = ceil_div(Cin, pl.cin_t);
+  pl.R = 256 / pl.cin_t;
+  if (pl.R < 1) pl.R = 1;
+  int64_t nb = (int64_t)sm_count_cached() * 4 / pl.cin_tiles;
+  const int64_t maxb = rows / ((int64_t)pl.R * 8);
+  if (nb > maxb) nb = maxb;
+  if (nb < 1) nb = 1;
+  pl.rows_per_block = ceil_div64(rows, nb);
+  pl.nblocks = (int)ceil_div64(rows, pl.rows_per_block);
+  return pl;
+}
+
+}  // namespace mednet
+
+using namespace mednet;
+
+extern "C" int mednet_conv1x1_fwd(const mednet_conv1_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->w && p->bias && p->y && p->N > 0 && p->S > 0 && p->Cin > 0 && p->Cout > 0,
+                 MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  const size_t smem = (size_t)p->Cin * p->Cout * sizeof(float);
+  MEDNET_REQUIRE(smem <= 48 * 1024, MEDNET_EUNSUPPORTED);
+  const int V = pick_vec(p->Cin, dtype_bytes(p->dtype));
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    conv1_fwd_kernel<T, VV><<<grid_for(p->N * p->S, 128, 16), 128, smem, stream>>>((const T*)p->x, p->w, p->bias, p->y,
+                                                                                  p->N, p->S, p->Cin, p->Cout);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" size_t mednet_conv1x1_bwd_workspace_bytes(const mednet_conv1_bwd_params* p) {
+  if (!p || p->Cin <= 0 || p->Cout <= 0) return 0;
+  Conv1Plan pl = conv1_plan(p->N * p->S, p->Cin);
+  return align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256) +
+         align_up((size_t)pl.nblocks * p->Cout * sizeof(float), 256);
+}
+
+extern "C" int mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* workspace, size_t workspace_bytes,
+                                  mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->w && p->dy && p->dw && p->db && p->N > 0 && p->S > 0 && p->Cin > 0 && p->Cout > 0,
+                 MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_conv1x1_bwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  const size_t smem = (size_t)p->Cin * p->Cout * sizeof(float);
+  MEDNET_REQUIRE(smem <= 48 * 1024, MEDNET_EUNSUPPORTED);
+  const int V = pick_vec(p->Cin, dtype_bytes(p->dtype));
+  if (p->dx != nullptr) {
+    MEDNET_DISPATCH_TV(p->dtype, V, {
+      conv1_dx_kernel<T, VV><<<grid_for(p->N * p->S, 128, 16), 128, smem, stream>>>(p->dy, p->w, (T*)p->dx, p->N, p->S,
+                                                                                   p->Cin, p->Cout);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  Conv1Plan pl = conv1_plan(p->N * p->S, p->Cin);
+  float* partial = (float*)workspace;
+  float* partial_b = (float*)((char*)workspace + align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256));
+  dim3 grid(pl.nblocks, pl.cin_tiles), block(pl.cin_t, pl.R);
+  const size_t sm2 = (size_t)pl.cin_t * pl.R * DW_MAX_CO * sizeof(float);
+  for (int co0 = 0; co0 < p->Cout; co0 += DW_MAX_CO) {
+    if (p->dtype == MEDNET_F32)
+      conv1_dw_partial_kernel<float><<<grid, block, sm2, stream>>>((const float*)p->x, p->dy, partial, p->N, p->S, p->Cin,
+                                                                  p->Cout, co0, pl.rows_per_block);
+    else
+      conv1_dw_partial_kernel<bf16><<<grid, block, sm2, stream>>>((const bf16*)p->x, p->dy, partial, p->N, p->S, p->Cin,
+                                                                 p->Cout, co0, pl.rows_per_block);
+    MEDNET_LAUNCH_CHECK();
+  }
+  conv1_db_partial_kernel<<<pl.nblocks, 256, 0, stream>>>(p->dy, partial_b, p->N, p->S, p->Cout, pl.rows_per_block);
+  MEDNET_LAUNCH_CHECK();
+  const int tot = p->Cout * p->Cin + p->Cout;
+  conv1_dw_final_kernel<<<ceil_div(tot, 128), 128, 0, stream>>>(partial, partial_b, p->dw, p->db, p->Cin, p->Cout,
+                                                               pl.nblocks, p->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}

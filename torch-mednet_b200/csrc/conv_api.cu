@@ -1,0 +1,78 @@
+// Dispatch of the 3x3x3 convolution entry points between the tcgen05 tensor-core kernels
+// (conv_tcgen05.cu) and the CUDA-core gather implicit GEMM (conv_simt.cu).  There is no fallback in the
+// silent sense: MEDNET_IMPL_AUTO resolves deterministically from shape/dtype/device, an explicit impl
+// that cannot take the problem returns MEDNET_EUNSUPPORTED.
+#include "common.cuh"
+#include "conv_impl.h"
+
+using namespace mednet;
+
+static bool conv_args_ok(const mednet_conv3d_params* p) {
+  return p && p->x && p->w && p->y && p->N > 0 && p->Di > 0 && p->Hi > 0 && p->Wi > 0 && p->Do > 0 && p->Ho > 0 &&
+         p->Wo > 0 && p->K > 0 && p->Nout > 0 && dtype_ok(p->dtype) && p->gather >= 0 && p->gather <= 2;
+}
+
+extern "C" int mednet_conv3d_select_impl(const mednet_conv3d_params* p) {
+  if (!p) return MEDNET_EINVAL;
+  if (p->impl == MEDNET_IMPL_SIMT) return MEDNET_IMPL_SIMT;
+  const bool tc = tc_fprop_supported(p);
+  if (p->impl == MEDNET_IMPL_TCGEN05) return tc ? MEDNET_IMPL_TCGEN05 : MEDNET_EUNSUPPORTED;
+  return tc ? MEDNET_IMPL_TCGEN05 : MEDNET_IMPL_SIMT;
+}
+
+extern "C" size_t mednet_conv3d_workspace_bytes(const mednet_conv3d_params* p) {
+  (void)p;
+  return 256;
+}
+
+extern "C" int mednet_conv3d_fprop(const mednet_conv3d_params* p, void* workspace, size_t workspace_bytes,
+                                   mednet_stream_t stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  MEDNET_REQUIRE(conv_args_ok(p), MEDNET_EINVAL);
+  if (p->gather == MEDNET_GATHER_CONV3)
+    MEDNET_REQUIRE(p->Di == p->Do && p->Hi == p->Ho && p->Wi == p->Wo, MEDNET_EINVAL);
+  else if (p->gather == MEDNET_GATHER_CONVT_F)
+    MEDNET_REQUIRE(p->Do == 2 * p->Di && p->Ho == 2 * p->Hi && p->Wo == 2 * p->Wi, MEDNET_EINVAL);
+  else
+    MEDNET_REQUIRE(p->Di == 2 * p->Do && p->Hi == 2 * p->Ho && p->Wi == 2 * p->Wo, MEDNET_EINVAL);
+  const int impl = mednet_conv3d_select_impl(p);
+  if (impl < 0) return impl;
+  if (impl == MEDNET_IMPL_TCGEN05) return tc_fprop(p, stream);
+  return simt_fprop(p, stream);
+}
+
+static bool wgrad_args_ok(const mednet_wgrad_params* p) {
+  return p && p->a && p->b && p->dw && p->N > 0 && p->Da > 0 && p->Ha > 0 && p->Wa > 0 && p->Db > 0 && p->Hb > 0 &&
+         p->Wb > 0 && p->Ca > 0 && p->Cb > 0 && dtype_ok(p->dtype) &&
+         (p->gather == MEDNET_GATHER_CONV3 || p->gather == MEDNET_GATHER_CONVT_B);
+}
+
+extern "C" int mednet_conv3d_wgrad_select_impl(const mednet_wgrad_params* p) {
+  if (!p) return MEDNET_EINVAL;
+  if (p->impl == MEDNET_IMPL_SIMT) return MEDNET_IMPL_SIMT;
+  const bool tc = tc_wgrad_supported(p);
+  if (p->impl == MEDNET_IMPL_TCGEN05) return tc ? MEDNET_IMPL_TCGEN05 : MEDNET_EUNSUPPORTED;
+  return tc ? MEDNET_IMPL_TCGEN05 : MEDNET_IMPL_SIMT;
+}
+
+extern "C" size_t mednet_conv3d_wgrad_workspace_bytes(const mednet_wgrad_params* p) {
+  if (!wgrad_args_ok(p)) return 0;
+  const int impl = mednet_conv3d_wgrad_select_impl(p);
+  if (impl == MEDNET_IMPL_TCGEN05) return tc_wgrad_workspace_bytes(p);
+  return simt_wgrad_workspace_bytes(p);
+}
+
+extern "C" int mednet_conv3d_wgrad(const mednet_wgrad_params* p, void* workspace, size_t workspace_bytes,
+                                   mednet_stream_t stream) {
+  MEDNET_REQUIRE(wgrad_args_ok(p), MEDNET_EINVAL);
+  if (p->gather == MEDNET_GATHER_CONV3)
+    MEDNET_REQUIRE(p->Da == p->Db && p->Ha == p->Hb && p->Wa == p->Wb, MEDNET_EINVAL);
+  else
+    MEDNET_REQUIRE(p->Db == 2 * p->Da && p->Hb == 2 * p->Ha && p->Wb == 2 * p->Wa, MEDNET_EINVAL);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_conv3d_wgrad_workspace_bytes(p), MEDNET_EWORKSPACE);
+  const int impl = mednet_conv3d_wgrad_select_impl(p);
+  if (impl < 0) return impl;
+  if (impl == MEDNET_IMPL_TCGEN05) return tc_wgrad(p, workspace, stream);
+  return simt_wgrad(p, workspace, stream);
+}

@@ -1,0 +1,21 @@
+// Internal interfaces between the convolution dispatcher and its two implementations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "mednet_b200.h"
+
+namespace mednet {
+int simt_fprop(const mednet_conv3d_params* p, cudaStream_t st);
+int simt_wgrad(const mednet_wgrad_params* p, void* workspace, cudaStream_t st);
+size_t simt_wgrad_workspace_bytes(const mednet_wgrad_params* p);
+size_t colsum_workspace_bytes(const mednet_wgrad_params* p);
+int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int accumulate, void* workspace,
+                cudaStream_t st);
+
+bool tc_fprop_supported(const mednet_conv3d_params* p);
+int tc_fprop(const mednet_conv3d_params* p, cudaStream_t st);
+bool tc_wgrad_supported(const mednet_wgrad_params* p);
+size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params* p);
+int tc_wgrad(const mednet_wgrad_params* p, void* workspace, cudaStream_t st);
+}  // namespace mednet

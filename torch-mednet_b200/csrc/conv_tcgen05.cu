@@ -1,0 +1,457 @@
+// 3x3x3 convolution (stride 1, pad 1) as an NDHWC implicit GEMM on the 5th-generation tensor cores.
+// ref: midasmednet/unet/components.py:8-9 (nn.Conv3d) -- fprop, and dgrad through flipped/transposed
+// packed weights (MEDNET_WPACK_TC_DGRAD).
+//
+// Mapping.  One CTA computes an output brick of TD x 16 x 8 voxels (d,h,w) by Ntile output channels:
+// each d-plane of the brick is one UMMA accumulator (M = 128 voxels, N = Ntile) living in TMEM.
+//   A operand : for every 64/32/16-channel chunk the (TD+2) x 18 x 10 HALO of the brick is staged ONCE
+//               in shared memory by TMA (zero fill outside the volume = the conv padding).  The 27 taps
+//               are 27 shifted windows of that halo: same bytes, different UMMA descriptor start address
+//               (kh -> halo row pitch, kw -> one 128-byte voxel row, kd -> plane).  No im2col, no
+//               27x re-read from L2.
+//   B operand : weights [27][Nout][K], one [Ntile x chunk] K-major tile per tap streamed through a ring.
+//   D         : TD accumulators x (1 or 2) stages in TMEM; the epilogue (bias, addend, activation,
+//               bf16 pack, NDHWC store) of tile i overlaps the MMAs of tile i+1 (persistent CTAs).
+// Warp roles: 0 = halo TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+ TMEM alloc), 3..6 =
+// epilogue (one TMEM lane quadrant each).  All hand-offs are mbarriers; halo planes are released as soon
+// as their last kd phase has been issued so the next chunk's planes stream in under the current MMAs.
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_impl.h"
+#include "tc_common.cuh"
+
+namespace mednet {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// runtime-selectable A-operand addressing (see DESIGN.md "UMMA descriptor experiments")
+static int g_dense_halo = 0;        // 0: halo rows padded to a 16-voxel pitch, one TMA per (d,h) row
+                                    // 1: dense 10-voxel pitch, one TMA box per halo plane
+static int g_base_offset_mode = 1;  // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
+
+constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
+constexpr int MAX_PLANES = 6, MAX_BSTAGES = 8;
+constexpr int NUM_THREADS = 224;
+
+struct TcConv {
+  int N, D, H, W, K, Nout;
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int64_t num_tiles;
+  int TD, Ntile, nchunks, RB, pitch, per_row, bo_mode;
+  int plane_bytes, b_bytes, BS, acc_stages, tmem_cols;
+  int act;
+  float act_param;
+  const float* bias;
+  const bf16* addend;
+  bf16* y;
+};
+
+struct TileCoord {
+  int n, d0, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcConv& p, int64_t t) {
+  TileCoord c;
+  c.n0 = (int)(t % p.tiles_n) * p.Ntile; t /= p.tiles_n;
+  c.w0 = (int)(t % p.tiles_w) * TILE_W; t /= p.tiles_w;
+  c.h0 = (int)(t % p.tiles_h) * TILE_H; t /= p.tiles_h;
+  c.d0 = (int)(t % p.tiles_d) * p.TD;
+  c.n = (int)(t / p.tiles_d);
+  return c;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcConv p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = a_base + (size_t)(p.TD + 2) * p.plane_bytes;
+  uint64_t* bars = (uint64_t*)(b_base + (size_t)p.BS * p.b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_PLANES;
+  uint64_t* b_full = bars + 2 * MAX_PLANES;
+  uint64_t* b_empty = b_full + MAX_BSTAGES;
+  uint64_t* acc_full = b_empty + MAX_BSTAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = p.TD + 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nplanes; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.BS; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    tc::fence_barrier_init();
+    tc::tma_prefetch_desc(&map_x);
+    tc::tma_prefetch_desc(&map_w);
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int KC = p.RB / 2;
+
+  if (warp == 0) {
+    // ===================== halo (A) producer =====================
+    if (tc::elect_one()) {
+      uint32_t ait = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, t);
+        for (int c = 0; c < p.nchunks; ++c, ++ait) {
+          for (int pl = 0; pl < nplanes; ++pl) {
+            tc::mbar_wait(&a_empty[pl], (ait & 1u) ^ 1u);
+            tc::mbar_arrive_expect_tx(&a_full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
+            uint8_t* dst = a_base + (size_t)pl * p.plane_bytes;
+            if (p.per_row) {
+              for (int ph = 0; ph < HALO_H; ++ph)
+                tc::tma_load_5d(dst + (size_t)ph * p.pitch * p.RB, &map_x, &a_full[pl], c * KC, tc_.w0 - 1,
+                                tc_.h0 - 1 + ph, tc_.d0 - 1 + pl, tc_.n);
+            } else {
+              tc::tma_load_5d(dst, &map_x, &a_full[pl], c * KC, tc_.w0 - 1, tc_.h0 - 1, tc_.d0 - 1 + pl, tc_.n);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight (B) producer =====================
+    if (tc::elect_one()) {
+      uint32_t bit = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, t);
+        for (int c = 0; c < p.nchunks; ++c) {
+          for (int tap = 0; tap < 27; ++tap, ++bit) {
+            const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
+            tc::mbar_wait(&b_empty[st], ph ^ 1u);
+            tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(p.Ntile * p.RB));
+            tc::tma_load_2d(b_base + (size_t)st * p.b_bytes, &map_w, &b_full[st], c * KC, tap * p.Nout + tc_.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.Ntile, 0, 0);
+      const uint32_t layout = p.RB == 128 ? tc::SWZ_128B : (p.RB == 64 ? tc::SWZ_64B : tc::SWZ_32B);
+      const uint32_t a_sbo = (uint32_t)(p.pitch * p.RB), b_sbo = (uint32_t)(8 * p.RB);
+      const uint32_t a_u32 = tc::smem_u32(a_base), b_u32 = tc::smem_u32(b_base);
+      const int ksteps = p.RB / 32;
+      uint32_t ait = 0, bit = 0, tcount = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+        const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
+        tc::mbar_wait(&acc_empty[as], aph ^ 1u);
+        tc::tc_fence_after();
+        for (int c = 0; c < p.nchunks; ++c, ++ait) {
+          for (int kd = 0; kd < 3; ++kd) {
+            if (kd == 0) {
+              for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full[pl], ait & 1u);
+            } else {
+              tc::mbar_wait(&a_full[p.TD - 1 + kd], ait & 1u);
+            }
+            tc::tc_fence_after();
+            for (int khw = 0; khw < 9; ++khw, ++bit) {
+              const int kh = khw / 3, kw = khw - kh * 3;
+              const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
+              tc::mbar_wait(&b_full[st], ph);
+              tc::tc_fence_after();
+              const uint32_t b_addr = b_u32 + st * (uint32_t)p.b_bytes;
+              for (int dz = 0; dz < p.TD; ++dz) {
+                const uint32_t a_addr =
+                    a_u32 + (uint32_t)(dz + kd) * (uint32_t)p.plane_bytes + (uint32_t)((kh * p.pitch + kw) * p.RB);
+                const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+                const uint32_t d_tmem = tmem_base + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, a_sbo, bo, layout);
+                  const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, b_sbo, 0, layout);
+                  tc::umma_bf16(d_tmem, da, db, idesc, (c | kd | khw | k) != 0 ? 1u : 0u);
+                }
+              }
+              tc::umma_commit(&b_empty[st]);
+            }
+            // planes whose last tap phase is this kd can be refilled for the next chunk
+            if (kd < 2) {
+              tc::umma_commit(&a_empty[kd]);
+            } else {
+              for (int pl = 2; pl < nplanes; ++pl) tc::umma_commit(&a_empty[pl]);
+            }
+          }
+        }
+        tc::umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;            // accumulator row = voxel (h, w) of the brick plane
+    const int hh = m >> 3, ww = m & 7;
+    uint32_t tcount = 0;
+    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      const TileCoord tc_ = decode_tile(p, t);
+      const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
+      tc::mbar_wait(&acc_full[as], aph);
+      tc::tc_fence_after();
+      const int h = tc_.h0 + hh, w = tc_.w0 + ww;
+      for (int dz = 0; dz < p.TD; ++dz) {
+        const int d = tc_.d0 + dz;
+        const bool inb = d < p.D && h < p.H && w < p.W;
+        const int64_t vox = (((int64_t)tc_.n * p.D + d) * p.H + h) * p.W + w;
+        bf16* yrow = p.y + vox * p.Nout + tc_.n0;
+        const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
+        for (int j = 0; j < p.Ntile; j += 16) {
+          uint32_t r[16];
+          tc::tmem_ld_x16(taddr + (uint32_t)j, r);
+          tc::tmem_ld_wait();
+          if (inb) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + tc_.n0 + j + i);
+            }
+            if (arow != nullptr) {
+              float a0[8], a1[8];
+              load_vec<bf16, 8>(arow + j, a0);
+              load_vec<bf16, 8>(arow + j + 8, a1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[i] += a0[i]; v[8 + i] += a1[i]; }
+            }
+            float o0[8], o1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o0[i] = act_apply(v[i], p.act, p.act_param);
+              o1[i] = act_apply(v[8 + i], p.act, p.act_param);
+            }
+            store_vec<bf16, 8>(yrow + j, o0);
+            store_vec<bf16, 8>(yrow + j + 8, o1);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int pick_ntile(int Nout) {
+  if (Nout <= 256) return Nout;
+  for (int t = 256; t >= 16; t -= 16)
+    if (Nout % t == 0) return t;
+  return 0;
+}
+static int pick_row_bytes(int K) { return (K % 64 == 0) ? 128 : (K % 32 == 0) ? 64 : (K % 16 == 0) ? 32 : 0; }
+
+static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
+  TcConv p;
+  p.N = q->N; p.D = q->Do; p.H = q->Ho; p.W = q->Wo; p.K = q->K; p.Nout = q->Nout;
+  p.RB = pick_row_bytes(q->K);
+  p.Ntile = pick_ntile(q->Nout);
+  if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
+  p.nchunks = q->K / (p.RB / 2);
+  p.TD = q->Do >= 2 ? 2 : 1;
+  p.per_row = g_dense_halo ? 0 : 1;
+  p.pitch = g_dense_halo ? HALO_W : 16;
+  p.bo_mode = g_base_offset_mode;
+  p.plane_bytes = (int)align_up((size_t)HALO_H * p.pitch * p.RB, 1024);
+  p.b_bytes = (int)align_up((size_t)p.Ntile * p.RB, 1024);
+  const int budget = 227 * 1024 - 1024 - 1024;   // alignment slack + barrier block
+  int bs = (budget - (p.TD + 2) * p.plane_bytes) / p.b_bytes;
+  if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
+  if (bs < 2) return false;
+  p.BS = bs;
+  p.acc_stages = (2 * p.TD * p.Ntile <= 512) ? 2 : 1;
+  int cols = p.acc_stages * p.TD * p.Ntile, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  if (pow2 > 512) return false;
+  p.tmem_cols = pow2;
+  p.tiles_w = ceil_div(p.W, TILE_W);
+  p.tiles_h = ceil_div(p.H, TILE_H);
+  p.tiles_d = ceil_div(p.D, p.TD);
+  p.tiles_n = q->Nout / p.Ntile;
+  p.num_tiles = (int64_t)p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.act = q->act; p.act_param = q->act_param;
+  p.bias = q->bias; p.addend = (const bf16*)q->addend; p.y = (bf16*)q->y;
+  *out = p;
+  return true;
+}
+
+bool tc_fprop_supported(const mednet_conv3d_params* q) {
+  if (q->dtype != MEDNET_BF16 || q->gather != MEDNET_GATHER_CONV3) return false;
+  if (!mednet_device_has_tcgen05()) return false;
+  if (((uintptr_t)q->x | (uintptr_t)q->w | (uintptr_t)q->y | (uintptr_t)q->addend) & 15) return false;
+  TcConv p;
+  return plan_tc(q, &p);
+}
+
+int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
+  TcConv p;
+  if (!plan_tc(q, &p)) return MEDNET_EUNSUPPORTED;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return MEDNET_ENODRIVER;
+  const int KC = p.RB / 2;
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.K, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.W * p.K * 2, (cuuint64_t)p.H * p.W * p.K * 2,
+                             (cuuint64_t)p.D * p.H * p.W * p.K * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)HALO_W, (cuuint32_t)(p.per_row ? 1 : HALO_H), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(q->x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(p.RB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MEDNET_EUNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)27 * p.Nout};
+    cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)p.Ntile};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q->w), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(p.RB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MEDNET_EUNSUPPORTED;
+  }
+  const size_t smem = 1024 + (size_t)(p.TD + 2) * p.plane_bytes + (size_t)p.BS * p.b_bytes + 1024;
+  static std::mutex mu;
+  static size_t configured = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = smem;
+    }
+  }
+  int64_t grid = p.num_tiles < sm_count_cached() ? p.num_tiles : sm_count_cached();
+  conv3_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, st>>>(map_x, map_w, p);
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+// tensor-core weight gradient: not built yet -> the dispatcher routes wgrad to the SIMT kernel
+bool tc_wgrad_supported(const mednet_wgrad_params*) { return false; }
+size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params*) { return 0; }
+int tc_wgrad(const mednet_wgrad_params*, void*, cudaStream_t) { return MEDNET_EUNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------------
+// descriptor probe: D = A_window * I with A written by TMA (SW128), B = identity written by hand.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap map_a, int rows, int row_shift, int sbo_bytes, int bo_mode,
+             float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_s = smem;                               // rows x 128 B (<= 32 KB)
+  uint8_t* b_s = smem + 32768;                       // 64 x 128 B identity
+  uint64_t* bar = (uint64_t*)(b_s + 8192);
+  uint32_t* slot = (uint32_t*)(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::fence_barrier_init();
+  }
+  // identity B[n][k], K-major SW128: 16-byte chunk index XORed with (n & 7)
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int n = i >> 6, k = i & 63;
+    const int off = n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+    *reinterpret_cast<bf16*>(b_s + off) = __float2bfloat16_rn(n == k ? 1.f : 0.f);
+  }
+  tc::fence_proxy_async();
+  if (warp == 0) {
+    tc::tmem_alloc(slot, 64);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    tc::mbar_arrive_expect_tx(&bar[0], (uint32_t)(rows * 128));
+    tc::tma_load_2d(a_s, &map_a, &bar[0], 0, 0);
+    tc::mbar_wait(&bar[0], 0);
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t a_addr = tc::smem_u32(a_s) + (uint32_t)row_shift * 128u;
+    const uint32_t bo = bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, (uint32_t)sbo_bytes, bo, tc::SWZ_128B);
+      const uint64_t db = tc::make_smem_desc(tc::smem_u32(b_s) + k * 32, 16, 1024, 0, tc::SWZ_128B);
+      tc::umma_bf16(tmem, da, db, idesc, k != 0);
+    }
+    tc::umma_commit(&bar[1]);
+  }
+  __syncwarp();
+  tc::mbar_wait(&bar[1], 0);
+  tc::tc_fence_after();
+  const int m = warp * 32 + lane;
+  for (int j = 0; j < 64; j += 16) {
+    uint32_t r[16];
+    tc::tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[m * 64 + j + i] = __uint_as_float(r[i]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+}  // namespace mednet
+
+using namespace mednet;
+
+extern "C" int mednet_tcgen05_configure(int dense_halo, int base_offset_mode) {
+  g_dense_halo = dense_halo ? 1 : 0;
+  g_base_offset_mode = base_offset_mode ? 1 : 0;
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_tcgen05_probe(const void* a_bf16, int32_t rows, int32_t row_shift, int32_t sbo_bytes,
+                                    int32_t base_offset_mode, float* out, mednet_stream_t stream) {
+  MEDNET_REQUIRE(a_bf16 && out && rows > 0 && rows <= 256 && row_shift >= 0 && sbo_bytes > 0 && (sbo_bytes % 16) == 0,
+                 MEDNET_EINVAL);
+  MEDNET_REQUIRE(row_shift * 128 + 15 * sbo_bytes + 8 * 128 <= rows * 128, MEDNET_EINVAL);
+  if (!mednet_device_has_tcgen05()) return MEDNET_EUNSUPPORTED;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return MEDNET_ENODRIVER;
+  CUtensorMap map_a;
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)rows};
+  cuuint32_t estr[2] = {1, 1};
+  if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a_bf16), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return MEDNET_EUNSUPPORTED;
+  const size_t smem = 1024 + 32768 + 8192 + 64;
+  cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  probe_kernel<<<1, 128, smem, stream>>>(map_a, rows, row_shift, sbo_bytes, base_offset_mode, out);
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}

@@ -1,0 +1,314 @@
+// Encoder/decoder glue, NDHWC, all HBM-bound with 16-byte vector accesses along the channel axis:
+//   * layout/dtype conversion at the module boundary
+//   * MaxPool3d(2) with window-local argmax codes            (ref: midasmednet/unet/components.py:210,224)
+//   * nearest upsample fused with the skip concat            (ref: midasmednet/unet/components.py:277-280)
+#include "common.cuh"
+
+namespace mednet {
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion: NCDHW <-> NDHWC with dtype cast.  32x32 smem tile transpose over (C, S).
+// ------------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void transpose_cs_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t R, int64_t Ccols) {
+  // src is [n][R][Ccols] (row-major), dst is [n][Ccols][R]
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const TS* s = src + n * R * Ccols;
+  TD* d = dst + n * R * Ccols;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Ccols) tile[i][threadIdx.x] = to_f32<TS>(s[r * Ccols + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Ccols) d[c * R + r] = from_f32<TD>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TD>(to_f32<TS>(src[i]));
+}
+
+template <typename TS, typename TD>
+static int launch_layout(const mednet_layout_params* p, cudaStream_t st) {
+  if (p->C == 1) {  // both layouts coincide
+    cast_kernel<TS, TD><<<grid_for(p->N * p->S, 256), 256, 0, st>>>((const TS*)p->src, (TD*)p->dst, p->N * p->S);
+  } else {
+    const int64_t R = p->to_channels_last ? p->C : p->S;
+    const int64_t Cc = p->to_channels_last ? p->S : p->C;
+    MEDNET_REQUIRE(ceil_div64(R, 32) <= 65535 && p->N <= 65535, MEDNET_EUNSUPPORTED);
+    dim3 grid((unsigned)ceil_div64(Cc, 32), (unsigned)ceil_div64(R, 32), (unsigned)p->N), block(32, 8);
+    transpose_cs_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)p->src, (TD*)p->dst, R, Cc);
+  }
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max pool 2x2x2 / stride 2 / floor mode
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ idx, int N,
+                                   int D, int H, int W, int C) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2, ncol = C / V;
+  const int64_t total = (int64_t)N * Do * Ho * Wo * ncol;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncol);
+    int64_t t = i / ncol;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho); t /= Ho;
+    const int od = (int)(t % Do);
+    const int n = (int)(t / Do);
+    float best[V];
+    int code[V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+      const int64_t off = ((((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dy)) * W + (2 * ow + dx)) * C + cv * V;
+      float v[V];
+      load_vec<T, V>(x + off, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        // ATen rule: (val > max) || isnan(val) -> first maximum wins, NaN wins
+        if (k == 0 || v[j] > best[j] || v[j] != v[j]) {
+          best[j] = v[j];
+          code[j] = k;
+        }
+      }
+    }
+    const int64_t o = ((((int64_t)n * Do + od) * Ho + oh) * Wo + ow) * C + cv * V;
+    store_vec<T, V>(y + o, best);
+    union { typename RawVec<V>::type r; uint8_t b[V]; } u;
+#pragma unroll
+    for (int j = 0; j < V; ++j) u.b[j] = (uint8_t)code[j];
+    *reinterpret_cast<typename RawVec<V>::type*>(idx + o) = u.r;
+  }
+}
+
+template <typename T, int V>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
+                                   int N, int D, int H, int W, int C) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2, ncol = C / V;
+  const int64_t total = (int64_t)N * D * H * W * ncol;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncol);
+    int64_t t = i / ncol;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    float g[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) g[j] = 0.f;
+    const int od = d >> 1, oh = h >> 1, ow = w >> 1;
+    if (od < Do && oh < Ho && ow < Wo) {
+      const int64_t o = ((((int64_t)n * Do + od) * Ho + oh) * Wo + ow) * C + cv * V;
+      const int mine = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+      float gy[V];
+      load_vec<T, V>(dy + o, gy);
+      union { typename RawVec<V>::type r; uint8_t b[V]; } u;
+      u.r = *reinterpret_cast<const typename RawVec<V>::type*>(idx + o);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = (u.b[j] == mine) ? gy[j] : 0.f;
+    }
+    store_vec<T, V>(dx + i * V, g);
+  }
+}
+
+__global__ void pool_idx_i64_kernel(const uint8_t* __restrict__ idx, int64_t* __restrict__ out, int N, int D, int H,
+                                    int W, int C) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)N * C * Do * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates the NCDHW output
+    int64_t t = i;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho); t /= Ho;
+    const int od = (int)(t % Do); t /= Do;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const int k = idx[((((int64_t)n * Do + od) * Ho + oh) * Wo + ow) * C + c];
+    out[i] = ((int64_t)(2 * od + (k >> 2)) * H + (2 * oh + ((k >> 1) & 1))) * W + (2 * ow + (k & 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest upsample (+ concat).  ATen's legacy 'nearest' source index, computed in fp32 exactly as
+// upstream: src = min((int)floorf(dst * ((float)in / out)), in - 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  const int s = (int)floorf(__fmul_rn((float)dst, scale));
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+template <typename T, int V>
+__global__ void upcat_fwd_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ out, int N,
+                                 int D, int H, int W, int d, int h, int w, int Cs, int Cl) {
+  const int C = Cs + Cl, ncol = C / V, ncs = Cs / V;
+  const float sd = (float)d / (float)D, sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int64_t total = (int64_t)N * D * H * W * ncol;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncol);
+    const int64_t vox = i / ncol;
+    typedef typename RawVec<sizeof(T) * V>::type R;
+    R val;
+    if (cv < ncs) {
+      val = *reinterpret_cast<const R*>(skip + vox * Cs + cv * V);
+    } else {
+      int64_t t = vox;
+      const int x = (int)(t % W); t /= W;
+      const int y = (int)(t % H); t /= H;
+      const int z = (int)(t % D);
+      const int n = (int)(t / D);
+      const int64_t src = (((int64_t)n * d + nearest_src(z, sd, d)) * h + nearest_src(y, sh, h)) * w + nearest_src(x, sw, w);
+      val = *reinterpret_cast<const R*>(low + src * Cl + (cv - ncs) * V);
+    }
+    *reinterpret_cast<R*>(out + i * V) = val;
+  }
+}
+
+// first destination index whose source is >= s (the mapping is monotone non-decreasing)
+__device__ __forceinline__ int nearest_first_dst(int s, float scale, int in_size, int out_size) {
+  int g = (int)(((int64_t)s * out_size) / in_size);
+  if (g > out_size) g = out_size;
+  while (g > 0 && nearest_src(g - 1, scale, in_size) >= s) --g;
+  while (g < out_size && nearest_src(g, scale, in_size) < s) ++g;
+  return g;
+}
+
+template <typename T, int V>
+__global__ void upcat_bwd_skip_kernel(const T* __restrict__ dout, T* __restrict__ dskip, int64_t vox, int Cs, int Cl) {
+  const int ncs = Cs / V;
+  const int64_t total = vox * ncs;
+  const int C = Cs + Cl;
+  typedef typename RawVec<sizeof(T) * V>::type R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncs);
+    const int64_t v = i / ncs;
+    *reinterpret_cast<R*>(dskip + i * V) = *reinterpret_cast<const R*>(dout + v * C + cv * V);
+  }
+}
+
+template <typename T, int V>
+__global__ void upcat_bwd_low_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, int D, int H, int W,
+                                     int d, int h, int w, int Cs, int Cl) {
+  const int C = Cs + Cl, ncl = Cl / V;
+  const float sd = (float)d / (float)D, sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int64_t total = (int64_t)N * d * h * w * ncl;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncl);
+    int64_t t = i / ncl;
+    const int x = (int)(t % w); t /= w;
+    const int y = (int)(t % h); t /= h;
+    const int z = (int)(t % d);
+    const int n = (int)(t / d);
+    const int z0 = nearest_first_dst(z, sd, d, D), z1 = nearest_first_dst(z + 1, sd, d, D);
+    const int y0 = nearest_first_dst(y, sh, h, H), y1 = nearest_first_dst(y + 1, sh, h, H);
+    const int x0 = nearest_first_dst(x, sw, w, W), x1 = nearest_first_dst(x + 1, sw, w, W);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int zz = z0; zz < z1; ++zz)
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) {
+          float g[V];
+          load_vec<T, V>(dout + ((((int64_t)n * D + zz) * H + yy) * W + xx) * C + Cs + cv * V, g);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += g[j];
+        }
+    store_vec<T, V>(dlow + i * V, acc);
+  }
+}
+
+}  // namespace mednet
+
+using namespace mednet;
+
+extern "C" int mednet_layout_convert(const mednet_layout_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->src && p->dst && p->N > 0 && p->C > 0 && p->S > 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype), MEDNET_EUNSUPPORTED);
+  if (p->src_dtype == MEDNET_F32 && p->dst_dtype == MEDNET_F32) return launch_layout<float, float>(p, stream);
+  if (p->src_dtype == MEDNET_F32 && p->dst_dtype == MEDNET_BF16) return launch_layout<float, bf16>(p, stream);
+  if (p->src_dtype == MEDNET_BF16 && p->dst_dtype == MEDNET_F32) return launch_layout<bf16, float>(p, stream);
+  return launch_layout<bf16, bf16>(p, stream);
+}
+
+extern "C" int mednet_maxpool3d_fwd(const mednet_pool_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->y && p->idx, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->C > 0 && p->D >= 2 && p->H >= 2 && p->W >= 2, MEDNET_EINVAL);
+  const int V = pick_vec(p->C, dtype_bytes(p->dtype));
+  const int64_t total = (int64_t)p->N * (p->D / 2) * (p->H / 2) * (p->W / 2) * (p->C / V);
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    maxpool_fwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->x, (T*)p->y, p->idx, p->N, p->D,
+                                                                       p->H, p->W, p->C);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->dy && p->idx && p->dx, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->C > 0 && p->D >= 2 && p->H >= 2 && p->W >= 2, MEDNET_EINVAL);
+  const int V = pick_vec(p->C, dtype_bytes(p->dtype));
+  const int64_t total = (int64_t)p->N * p->D * p->H * p->W * (p->C / V);
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    maxpool_bwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->dy, p->idx, (T*)p->dx, p->N, p->D,
+                                                                       p->H, p->W, p->C);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_maxpool3d_indices_i64(const uint8_t* idx, int64_t* out, int32_t N, int32_t D, int32_t H,
+                                            int32_t W, int32_t C, mednet_stream_t stream) {
+  MEDNET_REQUIRE(idx && out && N > 0 && C > 0 && D >= 2 && H >= 2 && W >= 2, MEDNET_EINVAL);
+  const int64_t total = (int64_t)N * C * (D / 2) * (H / 2) * (W / 2);
+  pool_idx_i64_kernel<<<grid_for(total, 256), 256, 0, stream>>>(idx, out, N, D, H, W, C);
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_upsample_concat_fwd(const mednet_upcat_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->low && p->out && (p->skip || p->Cs == 0), MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->D > 0 && p->H > 0 && p->W > 0 && p->d > 0 && p->h > 0 && p->w > 0 && p->Cs >= 0 &&
+                     p->Cl > 0, MEDNET_EINVAL);
+  int V = pick_vec(p->Cl, dtype_bytes(p->dtype));
+  if (p->Cs > 0) { const int v2 = pick_vec(p->Cs, dtype_bytes(p->dtype)); if (v2 < V) V = v2; }
+  const int64_t total = (int64_t)p->N * p->D * p->H * p->W * ((p->Cs + p->Cl) / V);
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    upcat_fwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->skip, (const T*)p->low, (T*)p->out,
+                                                                     p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs,
+                                                                     p->Cl);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_upsample_concat_bwd(const mednet_upcat_bwd_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->dout && p->dlow && (p->dskip || p->Cs == 0), MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->D > 0 && p->H > 0 && p->W > 0 && p->d > 0 && p->h > 0 && p->w > 0 && p->Cs >= 0 &&
+                     p->Cl > 0, MEDNET_EINVAL);
+  int V = pick_vec(p->Cl, dtype_bytes(p->dtype));
+  if (p->Cs > 0) { const int v2 = pick_vec(p->Cs, dtype_bytes(p->dtype)); if (v2 < V) V = v2; }
+  const int64_t vox = (int64_t)p->N * p->D * p->H * p->W;
+  const int64_t tl = (int64_t)p->N * p->d * p->h * p->w * (p->Cl / V);
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    if (p->Cs > 0) {
+      upcat_bwd_skip_kernel<T, VV><<<grid_for(vox * (p->Cs / VV), 256), 256, 0, stream>>>((const T*)p->dout,
+                                                                                        (T*)p->dskip, vox, p->Cs, p->Cl);
+    }
+    upcat_bwd_low_kernel<T, VV><<<grid_for(tl, 256), 256, 0, stream>>>((const T*)p->dout, (T*)p->dlow, p->N, p->D, p->H,
+                                                                      p->W, p->d, p->h, p->w, p->Cs, p->Cl);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}

@@ -1,0 +1,431 @@
+// GroupNorm (+ residual + activation) forward/backward and stand-alone activations, NDHWC.
+// Replaces nn.GroupNorm / ReLU / LeakyReLU / ELU call sites of midasmednet/unet/components.py:35-57
+// and the residual add + non-linearity of :177-178.  All kernels are HBM-bound: 16-byte vector
+// accesses along the channel axis, per-thread register partials, deterministic two-stage reductions.
+#include "common.cuh"
+
+namespace mednet {
+
+// ------------------------------------------------------------------------------------------------
+// launch plan shared by stats / apply / backward kernels: block = (ncol_t, R) threads, thread (tx,ty)
+// owns channel vector `tx` and walks rows ty, ty+R, ... of its slab -> a block reads R consecutive
+// NDHWC rows per step (fully coalesced) and every thread always sees the same channels.
+// ------------------------------------------------------------------------------------------------
+struct SlabPlan {
+  int V, ncol, ncol_t, coltiles, R, nslab;
+  int64_t rows_per_slab;
+};
+
+static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes) {
+  SlabPlan p;
+  p.V = pick_vec(C, elem_bytes);
+  p.ncol = C / p.V;
+  if (p.ncol <= 256) {
+    p.ncol_t = p.ncol;
+    p.coltiles = 1;
+    p.R = 256 / p.ncol;
+    if (p.R < 1) p.R = 1;
+  } else {
+    p.ncol_t = 256;
+    p.coltiles = ceil_div(p.ncol, 256);
+    p.R = 1;
+  }
+  int64_t target = (int64_t)sm_count_cached() * 6;
+  int64_t nslab = target / (N * p.coltiles);
+  int64_t max_slab = S / ((int64_t)p.R * 4);
+  if (nslab > max_slab) nslab = max_slab;
+  if (nslab < 1) nslab = 1;
+  p.rows_per_slab = ceil_div64(S, nslab);
+  p.nslab = (int)ceil_div64(S, p.rows_per_slab);
+  return p;
+}
+
+// reduce NV per-thread floats across threadIdx.y; the result for value i lands in the thread with
+// (i % R == ty) which calls emit(i, total).
+template <int NV, typename Emit>
+__device__ __forceinline__ void reduce_over_y(const float (&vals)[NV], float* sm, Emit emit) {
+  const int bx = blockDim.x, R = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sm[(ty * bx + tx) * NV + i] = vals[i];
+  __syncthreads();
+  for (int i = ty; i < NV; i += R) {
+    float acc = 0.f;
+    for (int t = 0; t < R; ++t) acc += sm[(t * bx + tx) * NV + i];
+    emit(i, acc);
+  }
+}
+
+// partial[((n*nslab + slab)*2 + which)*C + c] : which 0 = sum x, 1 = sum x^2
+template <typename T, int V>
+__global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int64_t S, int C,
+                                  int ncol, int64_t rows_per_slab, int nslab) {
+  extern __shared__ float sm[];
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int64_t r0 = (int64_t)slab * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > S) r1 = S;
+  float acc[2 * V];
+#pragma unroll
+  for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
+  const bool active = col < ncol;
+  if (active) {
+    const T* base = x + (int64_t)n * S * C + (int64_t)col * V;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float v[V];
+      load_vec<T, V>(base + r * C, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        acc[i] += v[i];
+        acc[V + i] += v[i] * v[i];
+      }
+    }
+  }
+  float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
+  reduce_over_y<2 * V>(acc, sm, [&](int i, float total) {
+    if (active) out[(i / V) * C + col * V + (i % V)] = total;
+  });
+}
+
+// one block per (n, g): mean / rstd and the per-(n,c) affine table ab[n][0][c] = a, ab[n][1][c] = b
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ ab, int64_t S, int C, int G,
+                                   int nslab, float eps) {
+  __shared__ double scratch[32];
+  __shared__ float s_mean, s_rstd;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < nslab * cpg; i += blockDim.x) {
+    const int slab = i / cpg, c = g * cpg + i % cpg;
+    const float* p = partial + ((int64_t)n * nslab + slab) * 2 * C;
+    s += (double)p[c];
+    q += (double)p[C + c];
+  }
+  s = block_sum(s, scratch);
+  q = block_sum(q, scratch);
+  if (threadIdx.x == 0) {
+    const double m = (double)cpg * (double)S;
+    const double mu = s / m;
+    double var = q / m - mu * mu;
+    if (var < 0.0) var = 0.0;
+    s_mean = (float)mu;
+    s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mean[n * G + g] = s_mean;
+    rstd[n * G + g] = s_rstd;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    const int c = g * cpg + i;
+    const float a = gamma[c] * s_rstd;
+    ab[((int64_t)n * 2 + 0) * C + c] = a;
+    ab[((int64_t)n * 2 + 1) * C + c] = beta[c] - s_mean * a;
+  }
+}
+
+template <typename T, int V>
+__global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                const float* __restrict__ ab, int64_t S, int C, int ncol,
+                                int64_t rows_per_slab, int act, float act_param) {
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int64_t r0 = (int64_t)slab * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > S) r1 = S;
+  float a[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    a[i] = ab[((int64_t)n * 2 + 0) * C + col * V + i];
+    b[i] = ab[((int64_t)n * 2 + 1) * C + col * V + i];
+  }
+  const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float v[V];
+    load_vec<T, V>(x + base + r * C, v);
+    if (residual != nullptr) {
+      float rr[V];
+      load_vec<T, V>(residual + base + r * C, rr);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]) + rr[i], act, act_param);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]), act, act_param);
+    }
+    store_vec<T, V>(y + base + r * C, v);
+  }
+}
+
+// backward stage 1: per (n, slab, c): S1 = sum dyh, S2x = sum dyh * x, dyh = dy * act'(y)
+template <typename T, int V>
+__global__ void gn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y,
+                                      const T* __restrict__ dy, float* __restrict__ partial, int64_t S, int C,
+                                      int ncol, int64_t rows_per_slab, int nslab, int act, float act_param) {
+  extern __shared__ float sm[];
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int64_t r0 = (int64_t)slab * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > S) r1 = S;
+  float acc[2 * V];
+#pragma unroll
+  for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
+  const bool active = col < ncol;
+  if (active) {
+    const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float xv[V], gv[V];
+      load_vec<T, V>(x + base + r * C, xv);
+      load_vec<T, V>(dy + base + r * C, gv);
+      if (act != MEDNET_ACT_NONE) {
+        float yv[V];
+        load_vec<T, V>(y + base + r * C, yv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        acc[i] += gv[i];
+        acc[V + i] += gv[i] * xv[i];
+      }
+    }
+  }
+  float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
+  reduce_over_y<2 * V>(acc, sm, [&](int i, float total) {
+    if (active) out[(i / V) * C + col * V + (i % V)] = total;
+  });
+}
+
+// backward stage 2, one block per (n,g): coefficient table coef[n][{A,B,Cc}][c] with
+//   dx = A*dyh + B*x + Cc,   A = rstd*gamma, B = -rstd^2*DS/m, Cc = rstd^2*DS*mu/m - rstd*DB/m
+// and the per-sample parameter-gradient contributions dgb[n][0][c] = sum dyh*xhat, dgb[n][1][c] = sum dyh.
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       float* __restrict__ coef, float* __restrict__ dgb, int64_t S, int C,
+                                       int G, int nslab) {
+  __shared__ double scratch[32];
+  __shared__ double s_ds, s_db;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const double mu = (double)mean[n * G + g], rs = (double)rstd[n * G + g];
+  double ds = 0.0, db = 0.0;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    const int c = g * cpg + i;
+    double s1 = 0.0, s2x = 0.0;
+    for (int slab = 0; slab < nslab; ++slab) {
+      const float* p = partial + ((int64_t)n * nslab + slab) * 2 * C;
+      s1 += (double)p[c];
+      s2x += (double)p[C + c];
+    }
+    const double s2 = rs * (s2x - mu * s1);
+    dgb[((int64_t)n * 2 + 0) * C + c] = (float)s2;
+    dgb[((int64_t)n * 2 + 1) * C + c] = (float)s1;
+    ds += (double)gamma[c] * s2;
+    db += (double)gamma[c] * s1;
+  }
+  ds = block_sum(ds, scratch);
+  db = block_sum(db, scratch);
+  if (threadIdx.x == 0) {
+    s_ds = ds;
+    s_db = db;
+  }
+  __syncthreads();
+  const double m = (double)cpg * (double)S;
+  const double B = -rs * rs * s_ds / m;
+  const double Cc = rs * rs * s_ds * mu / m - rs * s_db / m;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    const int c = g * cpg + i;
+    coef[((int64_t)n * 3 + 0) * C + c] = (float)(rs * (double)gamma[c]);
+    coef[((int64_t)n * 3 + 1) * C + c] = (float)B;
+    coef[((int64_t)n * 3 + 2) * C + c] = (float)Cc;
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const float* __restrict__ dgb, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float dg = 0.f, dbv = 0.f;
+  for (int n = 0; n < N; ++n) {
+    dg += dgb[((int64_t)n * 2 + 0) * C + c];
+    dbv += dgb[((int64_t)n * 2 + 1) * C + c];
+  }
+  if (accumulate) {
+    dgamma[c] += dg;
+    dbeta[c] += dbv;
+  } else {
+    dgamma[c] = dg;
+    dbeta[c] = dbv;
+  }
+}
+
+template <typename T, int V>
+__global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                    const float* __restrict__ coef, T* __restrict__ dx,
+                                    T* __restrict__ dresidual, int64_t S, int C, int ncol,
+                                    int64_t rows_per_slab, int act, float act_param) {
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int64_t r0 = (int64_t)slab * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > S) r1 = S;
+  float A[V], B[V], Cc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    A[i] = coef[((int64_t)n * 3 + 0) * C + col * V + i];
+    B[i] = coef[((int64_t)n * 3 + 1) * C + col * V + i];
+    Cc[i] = coef[((int64_t)n * 3 + 2) * C + col * V + i];
+  }
+  const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float xv[V], gv[V];
+    load_vec<T, V>(x + base + r * C, xv);
+    load_vec<T, V>(dy + base + r * C, gv);
+    if (act != MEDNET_ACT_NONE) {
+      float yv[V];
+      load_vec<T, V>(y + base + r * C, yv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
+    }
+    if (dresidual != nullptr) store_vec<T, V>(dresidual + base + r * C, gv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i]));
+    store_vec<T, V>(dx + base + r * C, xv);
+  }
+}
+
+template <typename T, int V>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t nvec, int act, float a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[V];
+    load_vec<T, V>(x + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = act_apply(v[k], act, a);
+    store_vec<T, V>(y + i * V, v);
+  }
+}
+
+template <typename T, int V>
+__global__ void act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx,
+                               int64_t nvec, int act, float a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float yv[V], gv[V];
+    load_vec<T, V>(y + i * V, yv);
+    load_vec<T, V>(dy + i * V, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) gv[k] *= act_grad_from_out(yv[k], act, a);
+    store_vec<T, V>(dx + i * V, gv);
+  }
+}
+
+}  // namespace mednet
+
+using namespace mednet;
+
+extern "C" size_t mednet_groupnorm_fwd_workspace_bytes(const mednet_gn_fwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || p->C <= 0) return 0;
+  SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
+  return align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256) +
+         align_up((size_t)p->N * 2 * p->C * sizeof(float), 256);
+}
+
+extern "C" int mednet_groupnorm_fwd(const mednet_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
+                                    mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->y && p->gamma && p->beta && p->mean && p->rstd, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->S > 0 && p->C > 0 && p->G > 0 && p->C % p->G == 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->N <= 65535, MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_groupnorm_fwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
+  float* partial = (float*)workspace;
+  float* ab = (float*)((char*)workspace + align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256));
+  dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+  MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+    size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+    gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->x, partial, p->S, p->C, pl.ncol,
+                                                            pl.rows_per_slab, pl.nslab);
+  });
+  MEDNET_LAUNCH_CHECK();
+  gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(partial, p->gamma, p->beta, p->mean, p->rstd, ab,
+                                                                  p->S, p->C, p->G, pl.nslab, p->eps);
+  MEDNET_LAUNCH_CHECK();
+  MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+    gn_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->residual, (T*)p->y, ab, p->S,
+                                                       p->C, pl.ncol, pl.rows_per_slab, p->act, p->act_param);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" size_t mednet_groupnorm_bwd_workspace_bytes(const mednet_gn_bwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || p->C <= 0) return 0;
+  SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
+  return align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256) +
+         align_up((size_t)p->N * 3 * p->C * sizeof(float), 256) + align_up((size_t)p->N * 2 * p->C * sizeof(float), 256);
+}
+
+extern "C" int mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
+                                    mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->dy && p->gamma && p->mean && p->rstd && p->dx && p->dgamma && p->dbeta,
+                 MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->act == MEDNET_ACT_NONE || p->y != nullptr, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(p->N > 0 && p->S > 0 && p->C > 0 && p->G > 0 && p->C % p->G == 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->N <= 65535, MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_groupnorm_bwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
+  char* ws = (char*)workspace;
+  float* partial = (float*)ws;
+  ws += align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256);
+  float* coef = (float*)ws;
+  ws += align_up((size_t)p->N * 3 * p->C * sizeof(float), 256);
+  float* dgb = (float*)ws;
+  dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+  MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+    size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+    gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy,
+                                                                partial, p->S, p->C, pl.ncol, pl.rows_per_slab,
+                                                                pl.nslab, p->act, p->act_param);
+  });
+  MEDNET_LAUNCH_CHECK();
+  gn_bwd_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(partial, p->gamma, p->mean, p->rstd, coef, dgb,
+                                                                      p->S, p->C, p->G, pl.nslab);
+  MEDNET_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<ceil_div(p->C, 128), 128, 0, stream>>>(dgb, p->dgamma, p->dbeta, (int)p->N, p->C,
+                                                               p->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+    gn_bwd_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy, coef,
+                                                           (T*)p->dx, (T*)p->dresidual, p->S, p->C, pl.ncol,
+                                                           pl.rows_per_slab, p->act, p->act_param);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_act_fwd(const mednet_act_fwd_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->x && p->y && p->numel > 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  const int V = pick_vec(p->numel, dtype_bytes(p->dtype));
+  const int64_t nvec = p->numel / V;
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    act_fwd_kernel<T, VV><<<grid_for(nvec, 256), 256, 0, stream>>>((const T*)p->x, (T*)p->y, nvec, p->act, p->act_param);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_act_bwd(const mednet_act_bwd_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->y && p->dy && p->dx && p->numel > 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  const int V = pick_vec(p->numel, dtype_bytes(p->dtype));
+  const int64_t nvec = p->numel / V;
+  MEDNET_DISPATCH_TV(p->dtype, V, {
+    act_bwd_kernel<T, VV><<<grid_for(nvec, 256), 256, 0, stream>>>((const T*)p->y, (const T*)p->dy, (T*)p->dx, nvec,
+                                                                   p->act, p->act_param);
+  });
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
