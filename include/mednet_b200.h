@@ -362,17 +362,20 @@ typedef struct {
 int mednet_tile_scatter(const mednet_tile_scatter_params* p, mednet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * tcgen05 descriptor-semantics probe (diagnostics; see DESIGN.md "UMMA descriptor experiments").
- * Runs D = A_window * I for a shifted/strided window of a TMA-written SW128 tile and returns the
- * gathered rows so the host can tell which descriptor variants address correctly.
+ * tcgen05 addressing calibration (see DESIGN.md "UMMA descriptor experiments").
+ * The conv kernel reads its 27 taps as shifted windows of one TMA-written halo tile, i.e. with UMMA
+ * descriptors whose start address is not aligned to the swizzle atom.  The probe runs D = A_window * I
+ * for such a window (row_bytes = 128 / 64 / 32 selects the swizzle width; K = N = row_bytes / 2) and
+ * returns the rows the tensor core actually fetched; the Python side calls it once per process, picks a
+ * variant that addresses correctly and registers it with mednet_tcgen05_configure.  Until a variant is
+ * registered for a swizzle width the tensor-core path reports MEDNET_EUNSUPPORTED for it.
+ *   dense_halo = 1 -> 10-voxel halo row pitch, one TMA box per plane; 0 -> rows padded to 16 voxels.
+ *   base_offset_mode: 0 -> descriptor base_offset 0; 1 -> (start >> 7) & 7; 2 -> (start / row_bytes) & 7.
  * ---------------------------------------------------------------------------------------------- */
-/* Selects how the conv kernel addresses its halo tile: dense_halo = 1 -> 10-voxel row pitch, one TMA box
- * per plane; 0 -> rows padded to a 16-voxel pitch (stride between 8-row groups stays a multiple of the
- * swizzle atom).  base_offset_mode = 1 -> descriptor base_offset = (start_address >> 7) & 7, 0 -> 0. */
-int mednet_tcgen05_configure(int dense_halo, int base_offset_mode);
-int mednet_tcgen05_probe(const void* a_bf16 /* [rows][64] */, int32_t rows, int32_t row_shift,
-                         int32_t sbo_bytes, int32_t base_offset_mode, float* out /* [128][64] */,
-                         mednet_stream_t stream);
+int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_halo, int base_offset_mode);
+int mednet_tcgen05_probe(const void* a_bf16 /* [rows][row_bytes/2] */, int32_t row_bytes, int32_t rows,
+                         int32_t row_shift, int32_t sbo_bytes, int32_t base_offset_mode,
+                         float* out /* [128][row_bytes/2] */, mednet_stream_t stream);
 
 #ifdef __cplusplus
 }

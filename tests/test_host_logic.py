@@ -1,0 +1,107 @@
+"""CPU-only tests of the host-side mirror of the reference interface: module tree / state_dict keys,
+constructor errors, tiling geometry against the reference generator's golden output, and that the product
+refuses CPU tensors instead of falling back."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_dict_from
+from mednet_b200.dataset import SyntheticSegmentationDataset, grid_geometry, grid_patch_generator
+from mednet_b200.landmarks import LandmarkNet
+from mednet_b200.segmentation import SegmentationNet
+from mednet_b200.unet.components import SingleConv, create_conv
+from mednet_b200.unet.loss import DiceLoss
+from mednet_b200.unet.model import ResidualUNet3D, UNet3D
+
+
+def test_state_dict_keys_and_shapes_match_reference(golden):
+    g = golden("unet3d_small")
+    ref = {k: tuple(v.shape) for k, v in state_dict_from(g).items()}
+    net = UNet3D(1, 2, False, f_maps=[8, 16, 32])
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == ref
+    net.load_state_dict(state_dict_from(g))
+    g = golden("residual_small")
+    ref = {k: tuple(v.shape) for k, v in state_dict_from(g).items()}
+    net = ResidualUNet3D(1, 4, False, f_maps=[8, 16, 32])
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == ref
+    assert len(UNet3D(1, 2, False).state_dict()) == 44
+    assert len(ResidualUNet3D(1, 2, False, f_maps=32).state_dict()) == 91
+    for order in ("crg", "cl", "gce"):
+        g = golden("unet3d_orders")
+        ref = {k: tuple(v.shape) for k, v in state_dict_from(g, f"{order}.sd.").items()}
+        net = UNet3D(2, 3, False, f_maps=[8, 16], layer_order=order)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == ref
+
+
+def test_reference_attributes_and_defaults():
+    net = UNet3D(1, 2, False)
+    assert len(net.encoders) == 4 and len(net.decoders) == 3 and net.testing is False
+    assert net.final_conv.weight.shape == (2, 64, 1, 1, 1)
+    assert net.encoders[0].pooling is None and net.encoders[1].pooling is not None
+    assert net.encoders[0].basic_module.SingleConv1.groupnorm.num_groups == 1      # quirk Q13: C=1 < 8 groups
+    assert net.decoders[0].basic_module.SingleConv1.conv.weight.shape == (256, 768, 3, 3, 3)
+    res = ResidualUNet3D(1, 2, False)
+    assert len(res.encoders) == 5 and res.decoders[0].upsample.weight.shape == (512, 256, 3, 3, 3)
+    assert ResidualUNet3D(1, 2, False, skip_final_activation=True).final_activation is None
+    assert UNet3D(1, 2, False, testing=True).testing is True
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(AssertionError, match="Conv layer MUST be present"):
+        create_conv(4, 4, 3, "gr", 8)
+    with pytest.raises(AssertionError, match="Non-linearity cannot be the first"):
+        create_conv(4, 4, 3, "rc", 8)
+    with pytest.raises(ValueError, match="Unsupported layer type"):
+        create_conv(4, 4, 3, "cx", 8)
+    with pytest.raises(AssertionError, match="divisible by num_groups"):
+        create_conv(12, 12, 3, "gc", 8)
+    assert SingleConv(4, 8, order="gcr")._plan == [("g", 0), ("c", 1)]
+    assert SingleConv(4, 8, order="cge")._plan == [("c", 0), ("g", 3)]
+    assert SingleConv(4, 8, order="crg")._plan == [("c", 1), ("g", 0)]
+    assert SingleConv(4, 8, order="cl").conv.bias is not None and SingleConv(4, 8, order="gcr").conv.bias is None
+
+
+def test_default_init_matches_pytorch_conv3d_statistics():
+    torch.manual_seed(0)
+    mine = SingleConv(16, 32, order="cr").conv
+    ref = torch.nn.Conv3d(16, 32, 3, padding=1)
+    bound = 1 / (16 * 27) ** 0.5
+    assert mine.weight.abs().max() <= bound and mine.bias.abs().max() <= bound
+    assert abs(mine.weight.std().item() - ref.weight.std().item()) < 2e-3
+
+
+def test_no_cpu_fallback():
+    net = UNet3D(1, 2, False, f_maps=[8, 16])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 8, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DiceLoss()(torch.zeros(1, 2, 4, 4, 4), torch.zeros(1, 4, 4, 4, dtype=torch.long))
+
+
+def test_grid_geometry_matches_reference_generator(golden):
+    g = golden("tiling")
+    for tag in "abc":
+        img, (p, o) = g[f"{tag}.img"], g[f"{tag}.patch"]
+        _, _, _, origins = grid_geometry(img.shape[1:], [p] * 3, [o] * 3)
+        np.testing.assert_array_equal(origins, g[f"{tag}.pos"])
+        sums = [patch.astype(np.float64).sum() for patch, _, _ in grid_patch_generator(img, [p] * 3, [o] * 3, mode="constant")]
+        np.testing.assert_allclose(sums, g[f"{tag}.sums"], rtol=1e-12)
+    assert len(grid_geometry((512, 512, 400), [128] * 3, [16] * 3)[3]) == 180      # cfg-4 tile counts
+    assert len(grid_geometry((512, 512, 400), [128] * 3, [32] * 3)[3]) == 448
+
+
+def test_task_modules_construct_with_reference_hparams():
+    import argparse
+    hp = argparse.Namespace(in_channels=1, out_channels=2, fmaps=8, learning_rate=1e-3, num_workers=0, batch_size=2,
+                            loss="DICE", loss_weight=[0.05, 1.0])
+    seg = SegmentationNet(hp)
+    assert "loss.weight" in seg.state_dict()                                      # DiceLoss buffer key (loss.py:100)
+    p = LandmarkNet.add_model_specific_args(argparse.ArgumentParser())
+    a = p.parse_args([])
+    assert a.fmaps == 64 and a.loss_regression_weight == [0.001, 0.015, 0.015, 0.015, 0.001, 0.001]
+    a.fmaps, a.out_channels = 8, 8
+    lm = LandmarkNet(a)
+    assert lm.num_heatmaps == 6 and "loss_class.weight" in lm.state_dict()
+    ds = SyntheticSegmentationDataset(2, (8, 8, 8), num_classes=2, num_heatmaps=3)
+    item = ds[0]
+    assert item["data"].shape == (1, 8, 8, 8) and item["label"].shape == (4, 8, 8, 8) and item["label"].dtype == torch.uint8

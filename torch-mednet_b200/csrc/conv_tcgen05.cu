@@ -37,10 +37,14 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// runtime-selectable A-operand addressing (see DESIGN.md "UMMA descriptor experiments")
-static int g_dense_halo = 0;        // 0: halo rows padded to a 16-voxel pitch, one TMA per (d,h) row
-                                    // 1: dense 10-voxel pitch, one TMA box per halo plane
-static int g_base_offset_mode = 1;  // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
+// runtime-selectable A-operand addressing per swizzle width (index: 0 = 128 B rows, 1 = 64 B, 2 = 32 B);
+// filled in by mednet_tcgen05_configure after the descriptor probe has run (see DESIGN.md
+// "UMMA descriptor experiments").  Until then the tensor-core path reports "unsupported".
+static int g_enabled[3] = {0, 0, 0};
+static int g_dense_halo[3] = {0, 0, 0};        // 0: halo rows padded to a 16-voxel pitch, one TMA per (d,h) row
+                                               // 1: dense 10-voxel pitch, one TMA box per halo plane
+static int g_base_offset_mode[3] = {1, 1, 1};  // 0: base_offset = 0; 1: (addr >> 7) & 7; 2: (addr / row_bytes) & 7
+static inline int rb_class(int rb) { return rb == 128 ? 0 : rb == 64 ? 1 : 2; }
 
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
 constexpr int MAX_PLANES = 6, MAX_BSTAGES = 8;
@@ -176,7 +180,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               for (int dz = 0; dz < p.TD; ++dz) {
                 const uint32_t a_addr =
                     a_u32 + (uint32_t)(dz + kd) * (uint32_t)p.plane_bytes + (uint32_t)((kh * p.pitch + kw) * p.RB);
-                const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+                const uint32_t bo = p.bo_mode == 0 ? 0u : (p.bo_mode == 1 ? ((a_addr >> 7) & 7u) : ((a_addr / (uint32_t)p.RB) & 7u));
                 const uint32_t d_tmem = tmem_base + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
                 for (int k = 0; k < ksteps; ++k) {
                   const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, a_sbo, bo, layout);
@@ -273,9 +277,11 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
   p.nchunks = q->K / (p.RB / 2);
   p.TD = q->Do >= 2 ? 2 : 1;
-  p.per_row = g_dense_halo ? 0 : 1;
-  p.pitch = g_dense_halo ? HALO_W : 16;
-  p.bo_mode = g_base_offset_mode;
+  const int rc = rb_class(p.RB);
+  if (!g_enabled[rc]) return false;
+  p.per_row = g_dense_halo[rc] ? 0 : 1;
+  p.pitch = g_dense_halo[rc] ? HALO_W : 16;
+  p.bo_mode = g_base_offset_mode[rc];
   p.plane_bytes = (int)align_up((size_t)HALO_H * p.pitch * p.RB, 1024);
   p.b_bytes = (int)align_up((size_t)p.Ntile * p.RB, 1024);
   const int budget = 227 * 1024 - 1024 - 1024;   // alignment slack + barrier block
@@ -358,27 +364,32 @@ size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params*) { return 0; }
 int tc_wgrad(const mednet_wgrad_params*, void*, cudaStream_t) { return MEDNET_EUNSUPPORTED; }
 
 // ------------------------------------------------------------------------------------------------
-// descriptor probe: D = A_window * I with A written by TMA (SW128), B = identity written by hand.
+// descriptor probe: D = A_window * I with A written by TMA (swizzle = row bytes), B = identity written
+// by hand in the canonical K-major swizzled layout.  K = row_bytes / 2 elements, N = K.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const __grid_constant__ CUtensorMap map_a, int rows, int row_shift, int sbo_bytes, int bo_mode,
+probe_kernel(const __grid_constant__ CUtensorMap map_a, int rb, int rows, int row_shift, int sbo_bytes, int bo_mode,
              float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_s = smem;                               // rows x 128 B (<= 32 KB)
-  uint8_t* b_s = smem + 32768;                       // 64 x 128 B identity
+  uint8_t* a_s = smem;                               // rows x rb bytes (<= 32 KB)
+  uint8_t* b_s = smem + 32768;                       // K x rb bytes identity
   uint64_t* bar = (uint64_t*)(b_s + 8192);
   uint32_t* slot = (uint32_t*)(bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = rb / 2;
+  const int chunks = rb / 16;                        // 16-byte chunks per row: 8 / 4 / 2
   if (threadIdx.x == 0) {
     tc::mbar_init(&bar[0], 1);
     tc::mbar_init(&bar[1], 1);
     tc::fence_barrier_init();
   }
-  // identity B[n][k], K-major SW128: 16-byte chunk index XORed with (n & 7)
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-    const int n = i >> 6, k = i & 63;
-    const int off = n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+  // identity B[n][k]: row n at n*rb, 16-byte chunk index XORed with the row's swizzle phase
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    const int row_off = n * rb;
+    const int phase = (row_off >> 7) & (chunks - 1);
+    const int off = row_off + ((((k >> 3) ^ phase) & (chunks - 1)) << 4) + (k & 7) * 2;
     *reinterpret_cast<bf16*>(b_s + off) = __float2bfloat16_rn(n == k ? 1.f : 0.f);
   }
   tc::fence_proxy_async();
@@ -391,16 +402,17 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, int rows, int row_shift,
   tc::tc_fence_after();
   const uint32_t tmem = *slot;
   if (threadIdx.x == 0) {
-    tc::mbar_arrive_expect_tx(&bar[0], (uint32_t)(rows * 128));
+    tc::mbar_arrive_expect_tx(&bar[0], (uint32_t)(rows * rb));
     tc::tma_load_2d(a_s, &map_a, &bar[0], 0, 0);
     tc::mbar_wait(&bar[0], 0);
     tc::tc_fence_after();
-    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
-    const uint32_t a_addr = tc::smem_u32(a_s) + (uint32_t)row_shift * 128u;
-    const uint32_t bo = bo_mode ? ((a_addr >> 7) & 7u) : 0u;
-    for (int k = 0; k < 4; ++k) {
-      const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, (uint32_t)sbo_bytes, bo, tc::SWZ_128B);
-      const uint64_t db = tc::make_smem_desc(tc::smem_u32(b_s) + k * 32, 16, 1024, 0, tc::SWZ_128B);
+    const uint32_t idesc = tc::make_idesc_bf16(128, K, 0, 0);
+    const uint32_t layout = rb == 128 ? tc::SWZ_128B : (rb == 64 ? tc::SWZ_64B : tc::SWZ_32B);
+    const uint32_t a_addr = tc::smem_u32(a_s) + (uint32_t)(row_shift * rb);
+    const uint32_t bo = bo_mode == 0 ? 0u : (bo_mode == 1 ? ((a_addr >> 7) & 7u) : ((a_addr / (uint32_t)rb) & 7u));
+    for (int k = 0; k < rb / 32; ++k) {
+      const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, (uint32_t)sbo_bytes, bo, layout);
+      const uint64_t db = tc::make_smem_desc(tc::smem_u32(b_s) + k * 32, 16, (uint32_t)(8 * rb), 0, layout);
       tc::umma_bf16(tmem, da, db, idesc, k != 0);
     }
     tc::umma_commit(&bar[1]);
@@ -409,12 +421,12 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, int rows, int row_shift,
   tc::mbar_wait(&bar[1], 0);
   tc::tc_fence_after();
   const int m = warp * 32 + lane;
-  for (int j = 0; j < 64; j += 16) {
+  for (int j = 0; j < K; j += 16) {
     uint32_t r[16];
     tc::tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j, r);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) out[m * 64 + j + i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) out[m * K + j + i] = __uint_as_float(r[i]);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -425,33 +437,38 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, int rows, int row_shift,
 
 using namespace mednet;
 
-extern "C" int mednet_tcgen05_configure(int dense_halo, int base_offset_mode) {
-  g_dense_halo = dense_halo ? 1 : 0;
-  g_base_offset_mode = base_offset_mode ? 1 : 0;
+extern "C" int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_halo, int base_offset_mode) {
+  MEDNET_REQUIRE(row_bytes == 128 || row_bytes == 64 || row_bytes == 32, MEDNET_EINVAL);
+  MEDNET_REQUIRE(base_offset_mode >= 0 && base_offset_mode <= 2, MEDNET_EINVAL);
+  const int rc = rb_class(row_bytes);
+  g_enabled[rc] = enabled ? 1 : 0;
+  g_dense_halo[rc] = dense_halo ? 1 : 0;
+  g_base_offset_mode[rc] = base_offset_mode;
   return MEDNET_OK;
 }
 
-extern "C" int mednet_tcgen05_probe(const void* a_bf16, int32_t rows, int32_t row_shift, int32_t sbo_bytes,
-                                    int32_t base_offset_mode, float* out, mednet_stream_t stream) {
+extern "C" int mednet_tcgen05_probe(const void* a_bf16, int32_t row_bytes, int32_t rows, int32_t row_shift,
+                                    int32_t sbo_bytes, int32_t base_offset_mode, float* out, mednet_stream_t stream) {
   MEDNET_REQUIRE(a_bf16 && out && rows > 0 && rows <= 256 && row_shift >= 0 && sbo_bytes > 0 && (sbo_bytes % 16) == 0,
                  MEDNET_EINVAL);
-  MEDNET_REQUIRE(row_shift * 128 + 15 * sbo_bytes + 8 * 128 <= rows * 128, MEDNET_EINVAL);
+  MEDNET_REQUIRE(row_bytes == 128 || row_bytes == 64 || row_bytes == 32, MEDNET_EINVAL);
+  MEDNET_REQUIRE(row_shift * row_bytes + 15 * sbo_bytes + 8 * row_bytes <= rows * row_bytes, MEDNET_EINVAL);
   if (!mednet_device_has_tcgen05()) return MEDNET_EUNSUPPORTED;
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return MEDNET_ENODRIVER;
   CUtensorMap map_a;
-  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, (cuuint32_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(row_bytes / 2), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)rows};
   cuuint32_t estr[2] = {1, 1};
   if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a_bf16), dims, strides, box, estr,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_NONE,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return MEDNET_EUNSUPPORTED;
   const size_t smem = 1024 + 32768 + 8192 + 64;
   cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  probe_kernel<<<1, 128, smem, stream>>>(map_a, rows, row_shift, sbo_bytes, base_offset_mode, out);
+  probe_kernel<<<1, 128, smem, stream>>>(map_a, row_bytes, rows, row_shift, sbo_bytes, base_offset_mode, out);
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }

@@ -1,0 +1,73 @@
+"""Sliding-window tiling geometry of the reference (midasmednet/dataset.py:349-389, :444-474) and the
+synthetic datasets used for measurement.  The HDF5/zarr readers and the random-patch MedDataset
+(dataset.py:109-346) are host-side I/O and out of scope; the synthetic
+datasets emit batches with exactly MedDataset's dict contract (dataset.py:332-346).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+
+def grid_geometry(img_size, patch_size, patch_overlap):
+    """Tile grid of grid_patch_generator (dataset.py:366-389).
+
+    Returns (cropped_patch_size, n_patches, overhead, origins) where ``origins`` is an (T, 3) int32 array
+    of tile origins in PADDED coordinates, raster order over axes 0, 1, 2.  The padded image has
+    ``patch_overlap`` voxels in front and ``patch_overlap + overhead`` behind (a full extra crop when the
+    size divides evenly, quirk Q8 -- only positions matter, padding is applied lazily by the gather kernel).
+    """
+    img_size = np.asarray(img_size, dtype=np.int64)
+    patch_size = np.asarray(patch_size, dtype=np.int64)
+    patch_overlap = np.asarray(patch_overlap, dtype=np.int64)
+    cropped = patch_size - 2 * patch_overlap
+    if (cropped <= 0).any():
+        raise ValueError("patch_size must exceed 2 * patch_overlap")
+    n_patches = np.ceil(img_size / cropped).astype(np.int64)
+    overhead = cropped - img_size % cropped
+    pos = [np.arange(0, n_patches[k]) * cropped[k] for k in range(3)]
+    grid = np.stack(np.meshgrid(*pos, indexing="ij"), axis=-1).reshape(-1, 3)
+    return cropped, n_patches, overhead, grid.astype(np.int32)
+
+
+def grid_patch_generator(img, patch_size, patch_overlap, **kwargs):
+    """Host (NumPy) generator with the reference's signature and yield order; used by tests and by callers
+    that want tiles on the CPU.  The GPU predictor gathers tiles directly from the device-resident volume."""
+    patch_size = np.asarray(patch_size)
+    patch_overlap = np.asarray(patch_overlap)
+    _, _, overhead, origins = grid_geometry(img.shape[1:], patch_size, patch_overlap)
+    pads = [[0, 0]] + [[int(patch_overlap[k]), int(patch_overlap[k] + overhead[k])] for k in range(3)]
+    padded = np.pad(img, pads, **kwargs)
+    for count, idx in enumerate(origins):
+        end = idx + patch_size
+        yield padded[:, idx[0]:end[0], idx[1]:end[1], idx[2]:end[2]], idx.copy(), count
+
+
+class SyntheticSegmentationDataset(Dataset):
+    """Random patches with MedDataset's contract: {'data': (C,H,W,D) f32, 'label': (L+1,H,W,D) u8} with the
+    class map in the LAST label channel (dataset.py:322-336) and L optional uint8 Gaussian heatmaps."""
+
+    def __init__(self, length, patch_size, in_channels=1, num_classes=2, num_heatmaps=0, sigma=3.0, seed=0):
+        self.length, self.patch_size = length, tuple(patch_size)
+        self.in_channels, self.num_classes, self.num_heatmaps, self.sigma, self.seed = \
+            in_channels, num_classes, num_heatmaps, sigma, seed
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + i)
+        data = torch.randn((self.in_channels,) + self.patch_size, generator=g)
+        cls = torch.randint(0, self.num_classes, (1,) + self.patch_size, generator=g, dtype=torch.uint8)
+        if self.num_heatmaps:
+            pts = torch.rand(self.num_heatmaps, 3, generator=g) * torch.tensor(self.patch_size, dtype=torch.float32)
+            ax = [torch.arange(s, dtype=torch.float32) for s in self.patch_size]
+            r2 = ((ax[0][None, :, None, None] - pts[:, 0, None, None, None]) ** 2 +
+                  (ax[1][None, None, :, None] - pts[:, 1, None, None, None]) ** 2 +
+                  (ax[2][None, None, None, :] - pts[:, 2, None, None, None]) ** 2)
+            hm = (255.0 * torch.exp(-r2 / (2 * self.sigma ** 2))).to(torch.uint8)
+            label = torch.cat([hm, cls], dim=0)
+        else:
+            label = cls
+        return {"data": data, "label": label}

@@ -1,0 +1,726 @@
+"""Operator layer: thin launch wrappers over the C ABI (``k_*``) and the ``torch.autograd.Function``s
+that the modules compose.  PyTorch is used for device memory, streams and the autograd tape only --
+every arithmetic step is a kernel of libmednet_b200.so.  No fallback: CPU tensors raise.
+
+Activations are NDHWC-contiguous tensors of shape (N, D, H, W, C) in the compute dtype (bf16 or fp32).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _abi
+from ._abi import check, lib, make
+
+ACT = {None: 0, "none": 0, "r": 1, "relu": 1, "l": 2, "leaky": 2, "e": 3, "elu": 3}
+ACT_PARAM = {0: 0.0, 1: 0.0, 2: 0.1, 3: 1.0}            # LeakyReLU slope 0.1 (components.py:38), ELU alpha 1
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2, torch.int64: 3}
+IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
+
+launch_count = 0          # kernels-API calls issued (bench.py reads it for `gpu_launches`)
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"mednet_b200: unsupported dtype {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mednet_b200 kernels run on CUDA tensors only (no CPU fallback)")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# =============================================================================================
+# tcgen05 addressing calibration (once per process)
+# =============================================================================================
+tcgen05_variants = {}      # row_bytes -> dict(enabled, dense_halo, base_offset_mode) as registered with the library
+_tc_calibrated = False
+
+
+def _probe(a, rb, shift, sbo, bo_mode):
+    k = rb // 2
+    out = torch.full((128, k), -1.0, dtype=torch.float32, device=a.device)
+    r = lib().mednet_tcgen05_probe(a.data_ptr(), rb, a.shape[0], shift, sbo, bo_mode, out.data_ptr(), _stream())
+    check(r, "tcgen05_probe")
+    torch.cuda.synchronize()
+    return out
+
+
+def probe_report(device="cuda"):
+    """Runs every (swizzle width, pitch, base-offset) variant and returns {name: bool} -- diagnostics."""
+    report = {}
+    for rb in (128, 64, 32):
+        k = rb // 2
+        g = torch.Generator(device="cpu").manual_seed(rb)
+        a = torch.randint(0, 256, (256, k), generator=g).to(torch.bfloat16).to(device)
+        af = a.float()
+        rows = torch.arange(128, device=device)
+        for name, pitch, shifts in (("aligned", 8, (0, 8)), ("padded", 16, (1, 2, 8)), ("dense", 10, (1, 2, 11, 22))):
+            for bo in (1, 0, 2):
+                ok = True
+                for shift in shifts:
+                    got = _probe(a, rb, shift, pitch * rb, bo)
+                    want = af[shift + (rows // 8) * pitch + rows % 8]
+                    ok = ok and bool(torch.equal(got, want))
+                report[f"rb{rb}.{name}.bo{bo}"] = ok
+    return report
+
+
+def calibrate_tcgen05(force=False):
+    """Finds, per swizzle width, a descriptor variant under which shifted windows of a TMA-written tile are
+    addressed correctly and registers it with the library (mednet_tcgen05_configure).  Preference: dense
+    halo (one TMA box per plane, least shared memory) over padded rows."""
+    global _tc_calibrated
+    if _tc_calibrated and not force:
+        return tcgen05_variants
+    _tc_calibrated = True
+    if not torch.cuda.is_available() or not lib().mednet_device_has_tcgen05():
+        return tcgen05_variants
+    rep = probe_report()
+    for rb in (128, 64, 32):
+        choice = None
+        for name, dense in (("dense", 1), ("padded", 0)):
+            for bo in (1, 0, 2):
+                if rep[f"rb{rb}.{name}.bo{bo}"] and rep[f"rb{rb}.aligned.bo{bo}"]:
+                    choice = dict(enabled=1, dense_halo=dense, base_offset_mode=bo)
+                    break
+            if choice:
+                break
+        if choice is None:
+            choice = dict(enabled=0, dense_halo=0, base_offset_mode=1)
+            import warnings
+            warnings.warn(f"mednet_b200: no working tcgen05 descriptor variant for {rb}-byte rows; "
+                          "3x3x3 convolutions with that channel chunking run on the CUDA-core kernel")
+        check(lib().mednet_tcgen05_configure(rb, choice["enabled"], choice["dense_halo"], choice["base_offset_mode"]),
+              "tcgen05_configure")
+        tcgen05_variants[rb] = choice
+    tcgen05_variants["report"] = rep
+    return tcgen05_variants
+
+
+# =============================================================================================
+# launch wrappers
+# =============================================================================================
+def k_layout(src, to_channels_last, dst_dtype):
+    """NCDHW (N,C,D,H,W) <-> NDHWC (N,D,H,W,C) with dtype cast."""
+    _need_cuda(src)
+    src = src.contiguous()
+    if to_channels_last:
+        n, c = src.shape[0], src.shape[1]
+        sp = tuple(src.shape[2:])
+        dst = torch.empty((n,) + sp + (c,), dtype=dst_dtype, device=src.device)
+    else:
+        n, c = src.shape[0], src.shape[-1]
+        sp = tuple(src.shape[1:-1])
+        dst = torch.empty((n, c) + sp, dtype=dst_dtype, device=src.device)
+    s = 1
+    for v in sp:
+        s *= v
+    p = make("mednet_layout_params", src=_ptr(src), dst=_ptr(dst), N=n, C=c, S=s, src_dtype=_dt(src),
+             dst_dtype=_DT[dst_dtype], to_channels_last=int(to_channels_last))
+    check(lib().mednet_layout_convert(_abi.C.byref(p), _stream()), "layout_convert")
+    _count()
+    return dst
+
+
+def conv_select_impl(x_shape, out_sp, K, Nout, dtype, gather, impl, x_ptr=0, w_ptr=0, y_ptr=0):
+    n, di, hi, wi = x_shape[0], x_shape[1], x_shape[2], x_shape[3]
+    if dtype == torch.bfloat16 and impl != "simt":
+        calibrate_tcgen05()
+    p = make("mednet_conv3d_params", x=x_ptr, w=w_ptr, y=y_ptr, N=n, Di=di, Hi=hi, Wi=wi, Do=out_sp[0], Ho=out_sp[1],
+             Wo=out_sp[2], K=K, Nout=Nout, dtype=_DT[dtype], gather=gather, impl=IMPL[impl])
+    r = lib().mednet_conv3d_select_impl(_abi.C.byref(p))
+    if r < 0:
+        check(r, "conv3d_select_impl")
+    return r
+
+
+def k_pack_weights(w, cin, cout, dtype, layout, transposed=False):
+    _need_cuda(w)
+    w = w.detach().contiguous().float()
+    out = torch.empty(cin * cout * 27, dtype=dtype, device=w.device)
+    p = make("mednet_wpack_params", w_oidhw=_ptr(w), w_packed=_ptr(out), Cin=cin, Cout=cout, dtype=_DT[dtype],
+             layout=layout, transposed=int(transposed))
+    check(lib().mednet_conv3d_pack_weights(_abi.C.byref(p), _stream()), "conv3d_pack_weights")
+    _count()
+    return out
+
+
+def k_conv3(x, w_packed, nout, out_sp, gather, impl_id, bias=None, addend=None, act=0):
+    """y = act(gather_conv(x, w) + bias + addend); x (N,Di,Hi,Wi,K) -> y (N,Do,Ho,Wo,nout)."""
+    _need_cuda(x, w_packed)
+    n, di, hi, wi, k = x.shape
+    y = torch.empty((n,) + tuple(out_sp) + (nout,), dtype=x.dtype, device=x.device)
+    p = make("mednet_conv3d_params", x=_ptr(x), w=_ptr(w_packed), bias=_ptr(bias), addend=_ptr(addend), y=_ptr(y), N=n,
+             Di=di, Hi=hi, Wi=wi, Do=out_sp[0], Ho=out_sp[1], Wo=out_sp[2], K=k, Nout=nout, dtype=_dt(x), act=act,
+             act_param=ACT_PARAM[act], gather=gather, impl=impl_id)
+    ws = _ws(256, x.device)
+    check(lib().mednet_conv3d_fprop(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_fprop")
+    _count()
+    return y
+
+
+def k_wgrad(a, b, gather, impl="auto", want_bias=False):
+    """dw (Ca,Cb,3,3,3) fp32 = sum_rows a[row] (x) b[gather(row, tap)]; optional bias gradient."""
+    _need_cuda(a, b)
+    n, da, ha, wa, ca = a.shape
+    _, db, hb, wb, cb = b.shape
+    dw = torch.empty((ca, cb, 3, 3, 3), dtype=torch.float32, device=a.device)
+    nb = ca if gather == 0 else cb
+    dbias = torch.empty(nb, dtype=torch.float32, device=a.device) if want_bias else None
+    p = make("mednet_wgrad_params", a=_ptr(a), b=_ptr(b), dw=_ptr(dw), dbias=_ptr(dbias), N=n, Da=da, Ha=ha, Wa=wa, Db=db,
+             Hb=hb, Wb=wb, Ca=ca, Cb=cb, dtype=_dt(a), gather=gather, impl=IMPL[impl], accumulate=0)
+    ws = _ws(lib().mednet_conv3d_wgrad_workspace_bytes(_abi.C.byref(p)), a.device)
+    check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_wgrad")
+    _count(2)
+    return dw, dbias
+
+
+def k_conv1_fwd(x, w2d, bias):
+    _need_cuda(x, w2d, bias)
+    n, sp, cin = x.shape[0], tuple(x.shape[1:-1]), x.shape[-1]
+    cout = w2d.shape[0]
+    s = sp[0] * sp[1] * sp[2]
+    y = torch.empty((n, cout) + sp, dtype=torch.float32, device=x.device)
+    p = make("mednet_conv1_params", x=_ptr(x), w=_ptr(w2d), bias=_ptr(bias), y=_ptr(y), N=n, S=s, Cin=cin, Cout=cout,
+             dtype=_dt(x))
+    check(lib().mednet_conv1x1_fwd(_abi.C.byref(p), _stream()), "conv1x1_fwd")
+    _count()
+    return y
+
+
+def k_conv1_bwd(x, w2d, dy, need_dx=True):
+    _need_cuda(x, w2d, dy)
+    n, sp, cin = x.shape[0], tuple(x.shape[1:-1]), x.shape[-1]
+    cout = w2d.shape[0]
+    s = sp[0] * sp[1] * sp[2]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty((cout, cin), dtype=torch.float32, device=x.device)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device)
+    p = make("mednet_conv1_bwd_params", x=_ptr(x), w=_ptr(w2d), dy=_ptr(dy), dx=_ptr(dx), dw=_ptr(dw), db=_ptr(db), N=n,
+             S=s, Cin=cin, Cout=cout, dtype=_dt(x), accumulate=0)
+    ws = _ws(lib().mednet_conv1x1_bwd_workspace_bytes(_abi.C.byref(p)), x.device)
+    check(lib().mednet_conv1x1_bwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv1x1_bwd")
+    _count(4)
+    return dx, dw, db
+
+
+def k_gn_fwd(x, gamma, beta, groups, act=0, residual=None, eps=1e-5):
+    _need_cuda(x, gamma, beta)
+    n, c = x.shape[0], x.shape[-1]
+    s = x.numel() // (n * c)
+    y = torch.empty_like(x)
+    mean = torch.empty((n, groups), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((n, groups), dtype=torch.float32, device=x.device)
+    p = make("mednet_gn_fwd_params", x=_ptr(x), gamma=_ptr(gamma), beta=_ptr(beta), residual=_ptr(residual), y=_ptr(y),
+             mean=_ptr(mean), rstd=_ptr(rstd), N=n, S=s, C=c, G=groups, dtype=_dt(x), act=act,
+             act_param=ACT_PARAM[act], eps=eps)
+    ws = _ws(lib().mednet_groupnorm_fwd_workspace_bytes(_abi.C.byref(p)), x.device)
+    check(lib().mednet_groupnorm_fwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "groupnorm_fwd")
+    _count(3)
+    return y, mean, rstd
+
+
+def k_gn_bwd(x, y, dy, gamma, mean, rstd, groups, act=0, want_dresidual=False):
+    _need_cuda(x, dy)
+    n, c = x.shape[0], x.shape[-1]
+    s = x.numel() // (n * c)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dresidual else None
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    p = make("mednet_gn_bwd_params", x=_ptr(x), y=_ptr(y), dy=_ptr(dy), gamma=_ptr(gamma), mean=_ptr(mean),
+             rstd=_ptr(rstd), dx=_ptr(dx), dresidual=_ptr(dres), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta), N=n, S=s, C=c,
+             G=groups, dtype=_dt(x), act=act, act_param=ACT_PARAM[act], accumulate=0)
+    ws = _ws(lib().mednet_groupnorm_bwd_workspace_bytes(_abi.C.byref(p)), x.device)
+    check(lib().mednet_groupnorm_bwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "groupnorm_bwd")
+    _count(4)
+    return dx, dgamma, dbeta, dres
+
+
+def k_act_fwd(x, act):
+    _need_cuda(x)
+    y = torch.empty_like(x)
+    p = make("mednet_act_fwd_params", x=_ptr(x), y=_ptr(y), numel=x.numel(), dtype=_dt(x), act=act,
+             act_param=ACT_PARAM[act])
+    check(lib().mednet_act_fwd(_abi.C.byref(p), _stream()), "act_fwd")
+    _count()
+    return y
+
+
+def k_act_bwd(y, dy, act):
+    _need_cuda(y, dy)
+    dx = torch.empty_like(dy)
+    p = make("mednet_act_bwd_params", y=_ptr(y), dy=_ptr(dy), dx=_ptr(dx), numel=y.numel(), dtype=_dt(y), act=act,
+             act_param=ACT_PARAM[act])
+    check(lib().mednet_act_bwd(_abi.C.byref(p), _stream()), "act_bwd")
+    _count()
+    return dx
+
+
+def k_pool_fwd(x):
+    _need_cuda(x)
+    n, d, h, w, c = x.shape
+    y = torch.empty((n, d // 2, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    p = make("mednet_pool_params", x=_ptr(x), y=_ptr(y), idx=_ptr(idx), N=n, D=d, H=h, W=w, C=c, dtype=_dt(x))
+    check(lib().mednet_maxpool3d_fwd(_abi.C.byref(p), _stream()), "maxpool3d_fwd")
+    _count()
+    return y, idx
+
+
+def k_pool_bwd(dy, idx, in_shape):
+    _need_cuda(dy, idx)
+    n, d, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
+    p = make("mednet_pool_bwd_params", dy=_ptr(dy), idx=_ptr(idx), dx=_ptr(dx), N=n, D=d, H=h, W=w, C=c, dtype=_dt(dy))
+    check(lib().mednet_maxpool3d_bwd(_abi.C.byref(p), _stream()), "maxpool3d_bwd")
+    _count()
+    return dx
+
+
+def k_pool_indices_i64(idx, in_shape):
+    n, d, h, w, c = in_shape
+    out = torch.empty((n, c, d // 2, h // 2, w // 2), dtype=torch.int64, device=idx.device)
+    check(lib().mednet_maxpool3d_indices_i64(_ptr(idx), _ptr(out), n, d, h, w, c, _stream()), "maxpool3d_indices_i64")
+    _count()
+    return out
+
+
+def k_upcat_fwd(skip, low):
+    _need_cuda(skip, low)
+    n, D, H, W, cs = skip.shape
+    _, d, h, w, cl = low.shape
+    out = torch.empty((n, D, H, W, cs + cl), dtype=low.dtype, device=low.device)
+    p = make("mednet_upcat_params", skip=_ptr(skip), low=_ptr(low), out=_ptr(out), N=n, D=D, H=H, W=W, d=d, h=h, w=w,
+             Cs=cs, Cl=cl, dtype=_dt(low))
+    check(lib().mednet_upsample_concat_fwd(_abi.C.byref(p), _stream()), "upsample_concat_fwd")
+    _count()
+    return out
+
+
+def k_upcat_bwd(dout, skip_shape, low_shape):
+    _need_cuda(dout)
+    n, D, H, W, cs = skip_shape
+    _, d, h, w, cl = low_shape
+    dskip = torch.empty(skip_shape, dtype=dout.dtype, device=dout.device)
+    dlow = torch.empty(low_shape, dtype=dout.dtype, device=dout.device)
+    p = make("mednet_upcat_bwd_params", dout=_ptr(dout), dskip=_ptr(dskip), dlow=_ptr(dlow), N=n, D=D, H=H, W=W, d=d,
+             h=h, w=w, Cs=cs, Cl=cl, dtype=_dt(dout))
+    check(lib().mednet_upsample_concat_bwd(_abi.C.byref(p), _stream()), "upsample_concat_bwd")
+    _count(2)
+    return dskip, dlow
+
+
+def _logit_view(t):
+    """(N, C, *spatial) tensor (possibly a channel slice) -> (tensor, N, C, S, batch_stride)."""
+    n, c = t.shape[0], t.shape[1]
+    s = t.numel() // (n * c)
+    ok = t.dim() >= 3 and t[0, 0].is_contiguous() and (c == 1 or t.stride(1) == s)
+    if not ok:
+        t = t.contiguous()
+    return t, n, c, s, (t.stride(0) if n > 1 else c * s)
+
+
+def k_dice_fwd(logits, labels, weight, eps, sigmoid):
+    _need_cuda(logits, labels)
+    logits, n, c, s, bs = _logit_view(logits)
+    labels = labels.contiguous()
+    dev = logits.device
+    sums = torch.empty(3 * c, dtype=torch.float32, device=dev)
+    dice = torch.empty(c, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    p = make("mednet_dice_params", logits=_ptr(logits), labels=_ptr(labels), weight=_ptr(weight), sums=_ptr(sums),
+             dice=_ptr(dice), loss=_ptr(loss), N=n, S=s, batch_stride=bs, C=c, logits_dtype=_dt(logits),
+             label_dtype=_dt(labels), sigmoid=int(sigmoid), epsilon=eps)
+    ws = _ws(lib().mednet_dice_workspace_bytes(_abi.C.byref(p)), dev)
+    check(lib().mednet_dice_fwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "dice_fwd")
+    _count(2)
+    return loss, dice, sums, logits, labels
+
+
+def k_dice_bwd(logits, labels, weight, sums, grad_out, eps, sigmoid, out=None, out_batch_stride=None):
+    logits, n, c, s, bs = _logit_view(logits)
+    if out is None:
+        out = torch.empty((n, c) + tuple(logits.shape[2:]), dtype=torch.float32, device=logits.device)
+        out_batch_stride = c * s
+    p = make("mednet_dice_bwd_params", logits=_ptr(logits), labels=_ptr(labels), weight=_ptr(weight), sums=_ptr(sums),
+             grad_out=_ptr(grad_out), dlogits=_ptr(out), N=n, S=s, batch_stride=bs, batch_stride_out=out_batch_stride,
+             C=c, logits_dtype=_dt(logits), label_dtype=_dt(labels), dlogits_dtype=_dt(out), sigmoid=int(sigmoid),
+             epsilon=eps)
+    check(lib().mednet_dice_bwd(_abi.C.byref(p), _stream()), "dice_bwd")
+    _count()
+    return out
+
+
+def k_ce_fwd(logits, labels, weight):
+    _need_cuda(logits, labels)
+    logits, n, c, s, bs = _logit_view(logits)
+    labels = labels.contiguous()
+    dev = logits.device
+    sums = torch.empty(2, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    p = make("mednet_ce_params", logits=_ptr(logits), labels=_ptr(labels), weight=_ptr(weight), sums=_ptr(sums),
+             loss=_ptr(loss), N=n, S=s, batch_stride=bs, C=c, logits_dtype=_dt(logits), label_dtype=_dt(labels))
+    ws = _ws(lib().mednet_ce_workspace_bytes(_abi.C.byref(p)), dev)
+    check(lib().mednet_ce_fwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "ce_fwd")
+    _count(2)
+    return loss, sums, logits, labels
+
+
+def k_ce_bwd(logits, labels, weight, sums, grad_out, out=None, out_batch_stride=None):
+    logits, n, c, s, bs = _logit_view(logits)
+    if out is None:
+        out = torch.empty((n, c) + tuple(logits.shape[2:]), dtype=torch.float32, device=logits.device)
+        out_batch_stride = c * s
+    p = make("mednet_ce_bwd_params", logits=_ptr(logits), labels=_ptr(labels), weight=_ptr(weight), sums=_ptr(sums),
+             grad_out=_ptr(grad_out), dlogits=_ptr(out), N=n, S=s, batch_stride=bs, batch_stride_out=out_batch_stride,
+             C=c, logits_dtype=_dt(logits), label_dtype=_dt(labels), dlogits_dtype=_dt(out))
+    check(lib().mednet_ce_bwd(_abi.C.byref(p), _stream()), "ce_bwd")
+    _count()
+    return out
+
+
+def k_hm_fwd(pred, target, weight, l1):
+    _need_cuda(pred, target, weight)
+    pred, n, L, s, bs = _logit_view(pred)
+    target = target.contiguous()
+    dev = pred.device
+    per_channel = torch.empty(L, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    p = make("mednet_hmloss_params", pred=_ptr(pred), target=_ptr(target), weight=_ptr(weight),
+             per_channel=_ptr(per_channel), loss=_ptr(loss), N=n, S=s, batch_stride=bs, L=L, pred_dtype=_dt(pred),
+             target_dtype=_dt(target), l1=int(l1))
+    ws = _ws(lib().mednet_heatmap_loss_workspace_bytes(_abi.C.byref(p)), dev)
+    check(lib().mednet_heatmap_loss_fwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "heatmap_loss_fwd")
+    _count(2)
+    return loss, per_channel, pred, target
+
+
+def k_hm_bwd(pred, target, weight, grad_out, l1, out=None, out_batch_stride=None):
+    pred, n, L, s, bs = _logit_view(pred)
+    if out is None:
+        out = torch.empty((n, L) + tuple(pred.shape[2:]), dtype=torch.float32, device=pred.device)
+        out_batch_stride = L * s
+    p = make("mednet_hmloss_bwd_params", pred=_ptr(pred), target=_ptr(target), weight=_ptr(weight),
+             grad_out=_ptr(grad_out), dpred=_ptr(out), N=n, S=s, batch_stride=bs, batch_stride_out=out_batch_stride, L=L,
+             pred_dtype=_dt(pred), target_dtype=_dt(target), dpred_dtype=_dt(out), l1=int(l1))
+    check(lib().mednet_heatmap_loss_bwd(_abi.C.byref(p), _stream()), "heatmap_loss_bwd")
+    _count()
+    return out
+
+
+def k_predict_epilogue(logits, num_heatmaps):
+    """(N, L+K, *sp) float logits -> (N, L+1, *sp) uint8 (examples/predict.py:88-94)."""
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    n, c = logits.shape[0], logits.shape[1]
+    sp = tuple(logits.shape[2:])
+    s = logits.numel() // (n * c)
+    out = torch.empty((n, num_heatmaps + 1) + sp, dtype=torch.uint8, device=logits.device)
+    p = make("mednet_predict_params", logits=_ptr(logits), out=_ptr(out), N=n, S=s, L=num_heatmaps, K=c - num_heatmaps,
+             logits_dtype=_dt(logits))
+    check(lib().mednet_predict_epilogue(_abi.C.byref(p), _stream()), "predict_epilogue")
+    _count()
+    return out
+
+
+def k_final_activation(logits, sigmoid):
+    _need_cuda(logits)
+    logits = logits.contiguous().float()
+    n, c = logits.shape[0], logits.shape[1]
+    s = logits.numel() // (n * c)
+    out = torch.empty_like(logits)
+    check(lib().mednet_final_activation(_ptr(logits), _ptr(out), n, s, c, int(sigmoid), _stream()), "final_activation")
+    _count()
+    return out
+
+
+def k_adam(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    p = make("mednet_adam_params", param=_ptr(param), grad=_ptr(grad), exp_avg=_ptr(exp_avg),
+             exp_avg_sq=_ptr(exp_avg_sq), numel=param.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+             grad_scale=grad_scale, step=step)
+    check(lib().mednet_adam_step(_abi.C.byref(p), _stream()), "adam_step")
+    _count()
+
+
+# =============================================================================================
+# autograd Functions (NDHWC tensors in, NDHWC tensors out)
+# =============================================================================================
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """3x3x3 conv, stride 1, pad 1 with fused bias / addend / activation epilogue.
+    ref: midasmednet/unet/components.py:8-9 (+ :35-40 for the fused non-linearity)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, addend, act, impl):
+        x = _c(x)
+        cout, cin = weight.shape[0], weight.shape[1]
+        sp = tuple(x.shape[1:4])
+        impl_id = conv_select_impl(x.shape, sp, cin, cout, x.dtype, 0, impl, x.data_ptr(), 0, 0)
+        wp = k_pack_weights(weight, cin, cout, x.dtype, 2 if impl_id == 2 else 0)
+        add = _c(addend) if addend is not None else None
+        y = k_conv3(x, wp, cout, sp, 0, impl_id, bias=bias.detach().float() if bias is not None else None,
+                    addend=add, act=act)
+        ctx.save_for_backward(x, weight, y if act else None)
+        ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = act, impl, bias is not None, addend is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = _c(dy)
+        cout, cin = weight.shape[0], weight.shape[1]
+        dpre = k_act_bwd(y, dy, ctx.act) if ctx.act else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            sp = tuple(x.shape[1:4])
+            impl_id = conv_select_impl(dpre.shape, sp, cout, cin, dpre.dtype, 0, ctx.impl, dpre.data_ptr(), 0, 0)
+            wp = k_pack_weights(weight, cin, cout, dpre.dtype, 3 if impl_id == 2 else 1)
+            dx = k_conv3(dpre, wp, cin, sp, 0, impl_id)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = k_wgrad(dpre, x, 0, ctx.impl, want_bias=ctx.has_bias)
+        return dx, dw, db, (dpre if ctx.has_addend else None), None, None
+
+
+class ConvTranspose3x3Fn(torch.autograd.Function):
+    """ConvTranspose3d(k3, s2, p1, op1) + bias, fused with the summation join `x += encoder_features`.
+    ref: midasmednet/unet/components.py:259-264, 283-284."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, skip, impl):
+        x = _c(x)
+        cin, cout = weight.shape[0], weight.shape[1]
+        out_sp = tuple(2 * v for v in x.shape[1:4])
+        if skip is not None and tuple(skip.shape[1:4]) != out_sp:
+            raise RuntimeError(f"The size of tensor a {out_sp} must match the size of tensor b "
+                               f"{tuple(skip.shape[1:4])} (summation join, components.py:284)")
+        wp = k_pack_weights(weight, cin, cout, x.dtype, 0, transposed=True)
+        y = k_conv3(x, wp, cout, out_sp, 1, 1, bias=bias.detach().float() if bias is not None else None,
+                    addend=_c(skip) if skip is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.has_skip, ctx.impl = bias is not None, skip is not None, impl
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        cin, cout = weight.shape[0], weight.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = k_pack_weights(weight, cin, cout, dy.dtype, 1, transposed=True)
+            dx = k_conv3(dy, wp, cin, tuple(x.shape[1:4]), 2, 1)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = k_wgrad(x, dy, 2, "simt", want_bias=ctx.has_bias)
+        return dx, dw, db, (dy if ctx.has_skip else None), None
+
+
+class GroupNormActFn(torch.autograd.Function):
+    """GroupNorm (+ residual add) (+ activation).  ref: components.py:57, :36-40, :177-178."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, act, residual):
+        x = _c(x)
+        res = _c(residual) if residual is not None else None
+        g, b = gamma.detach().float(), beta.detach().float()
+        y, mean, rstd = k_gn_fwd(x, g, b, groups, act, res)
+        ctx.save_for_backward(x, y if act else None, g, mean, rstd)
+        ctx.groups, ctx.act, ctx.has_res = groups, act, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, g, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta, dres = k_gn_bwd(x, y, _c(dy), g, mean, rstd, ctx.groups, ctx.act, ctx.has_res)
+        return dx, dgamma, dbeta, None, None, dres
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        y = k_act_fwd(_c(x), act)
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return k_act_bwd(y, _c(dy), ctx.act), None
+
+
+class MaxPoolFn(torch.autograd.Function):
+    """MaxPool3d(2).  ref: components.py:210,224."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y, idx = k_pool_fwd(x)
+        ctx.save_for_backward(idx)
+        ctx.in_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return k_pool_bwd(_c(dy), idx, ctx.in_shape)
+
+
+class UpsampleConcatFn(torch.autograd.Function):
+    """F.interpolate(x, size=skip.shape[2:], 'nearest') + cat((skip, x), 1).  ref: components.py:277-280."""
+
+    @staticmethod
+    def forward(ctx, skip, low):
+        skip, low = _c(skip), _c(low)
+        ctx.shapes = (tuple(skip.shape), tuple(low.shape))
+        return k_upcat_fwd(skip, low)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dskip, dlow = k_upcat_bwd(_c(dout), *ctx.shapes)
+        return dskip, dlow
+
+
+class Conv1x1Fn(torch.autograd.Function):
+    """Final 1x1x1 conv with bias: NDHWC activations -> NCDHW fp32 logits.  ref: model.py:77,102."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        w2 = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+        y = k_conv1_fwd(x, w2, bias.detach().float().contiguous())
+        ctx.save_for_backward(x, w2)
+        ctx.wshape = tuple(weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2 = ctx.saved_tensors
+        dx, dw, db = k_conv1_bwd(x, w2, dy.contiguous().float(), need_dx=ctx.needs_input_grad[0])
+        return dx, dw.reshape(ctx.wshape), db
+
+
+class ToChannelsLastFn(torch.autograd.Function):
+    """(N,C,D,H,W) any float dtype -> (N,D,H,W,C) compute dtype."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        return k_layout(x, True, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return k_layout(_c(dy), False, ctx.src_dtype), None
+
+
+class DiceLossFn(torch.autograd.Function):
+    """Fused softmax|sigmoid + weighted soft Dice.  ref: midasmednet/unet/loss.py:114-130."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, eps, sigmoid):
+        loss, dice, sums, lg, lb = k_dice_fwd(logits, labels, weight, eps, sigmoid)
+        ctx.save_for_backward(lg, lb, weight, sums)
+        ctx.eps, ctx.sigmoid = eps, sigmoid
+        ctx.mark_non_differentiable(dice)
+        return loss, dice
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_dice):
+        lg, lb, weight, sums = ctx.saved_tensors
+        g = grad_loss.detach().float().contiguous()
+        return k_dice_bwd(lg, lb, weight, sums, g, ctx.eps, ctx.sigmoid).to(lg.dtype), None, None, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """Weighted-mean cross entropy.  ref: midasmednet/segmentation.py:49, landmarks.py:49."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight):
+        loss, sums, lg, lb = k_ce_fwd(logits, labels, weight)
+        ctx.save_for_backward(lg, lb, weight, sums)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lg, lb, weight, sums = ctx.saved_tensors
+        g = grad_loss.detach().float().contiguous()
+        return k_ce_bwd(lg, lb, weight, sums, g).to(lg.dtype), None, None
+
+
+class HeatmapLossFn(torch.autograd.Function):
+    """sum_c w_c * mean((o_c - h_c)^2 | |o_c - h_c|).  ref: midasmednet/landmarks.py:125-134."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, l1):
+        loss, per_channel, pr, tg = k_hm_fwd(pred, target, weight, l1)
+        ctx.save_for_backward(pr, tg, weight)
+        ctx.l1 = l1
+        ctx.mark_non_differentiable(per_channel)
+        return loss, per_channel
+
+    @staticmethod
+    def backward(ctx, grad_loss, _g):
+        pr, tg, weight = ctx.saved_tensors
+        g = grad_loss.detach().float().contiguous()
+        return k_hm_bwd(pr, tg, weight, g, ctx.l1).to(pr.dtype), None, None, None
+
+
+class LandmarkLossFn(torch.autograd.Function):
+    """The whole LandmarkNet.loss on the un-split network output: heatmap regression on channels [0,L),
+    Dice|CE on channels [L, L+K); one gradient tensor, no slice/pad copies.
+    ref: midasmednet/landmarks.py:74-75 (split), :125-134 (loss)."""
+
+    @staticmethod
+    def forward(ctx, outputs, labels, heatmaps, class_weight, reg_weight, use_ce, l1, eps):
+        L = heatmaps.shape[1]
+        outputs = outputs.contiguous()
+        hm_loss, per_channel, _, tg = k_hm_fwd(outputs[:, :L], heatmaps, reg_weight, l1)
+        if use_ce:
+            cls_loss, sums, _, lb = k_ce_fwd(outputs[:, L:], labels, class_weight)
+        else:
+            cls_loss, _dice, sums, _, lb = k_dice_fwd(outputs[:, L:], labels, class_weight, eps, False)
+        ctx.save_for_backward(outputs, lb, tg, class_weight, reg_weight, sums)
+        ctx.cfg = (L, use_ce, l1, eps)
+        total = hm_loss + cls_loss       # scalar add on device (torch op on two 0-d tensors: plumbing, not hot path)
+        return total, cls_loss, hm_loss
+
+    @staticmethod
+    def backward(ctx, g_total, g_cls, g_hm):
+        outputs, lb, tg, class_weight, reg_weight, sums = ctx.saved_tensors
+        L, use_ce, l1, eps = ctx.cfg
+        n, c = outputs.shape[0], outputs.shape[1]
+        s = outputs.numel() // (n * c)
+        zero = torch.zeros((), dtype=torch.float32, device=outputs.device)
+        gc = ((g_total if g_total is not None else zero) + (g_cls if g_cls is not None else zero)).float().contiguous()
+        gh = ((g_total if g_total is not None else zero) + (g_hm if g_hm is not None else zero)).float().contiguous()
+        d = torch.empty(outputs.shape, dtype=torch.float32, device=outputs.device)
+        k_hm_bwd(outputs[:, :L], tg, reg_weight, gh, l1, out=d[:, :L], out_batch_stride=c * s)
+        if use_ce:
+            k_ce_bwd(outputs[:, L:], lb, class_weight, sums, gc, out=d[:, L:], out_batch_stride=c * s)
+        else:
+            k_dice_bwd(outputs[:, L:], lb, class_weight, sums, gc, eps, False, out=d[:, L:], out_batch_stride=c * s)
+        return d.to(outputs.dtype), None, None, None, None, None, None, None

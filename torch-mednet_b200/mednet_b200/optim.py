@@ -1,0 +1,76 @@
+"""Fused Adam over one flat fp32 bucket (ref: torch.optim.Adam(self.parameters(), lr) at
+midasmednet/segmentation.py:119-120, landmarks.py:176-177 -- PyTorch defaults, no weight decay).
+
+All parameters are re-pointed into one contiguous buffer (and so are their gradients), so the optimiser
+step is a single kernel launch and the data-parallel all-reduce can work on bucket views of that buffer.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+        if weight_decay != 0:
+            raise NotImplementedError("the reference uses Adam without weight decay")
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._params = params
+        self._flat = self._flat_grad = self._m = self._v = None
+        self._step = 0
+        self.grad_scale = 1.0
+
+    # -- flat storage ---------------------------------------------------------------------------
+    def _materialize(self):
+        if self._flat is not None:
+            return
+        dev = self._params[0].device
+        total = sum(p.numel() for p in self._params)
+        self._flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._offsets = []
+        off = 0
+        with torch.no_grad():
+            for p in self._params:
+                n = p.numel()
+                view = self._flat[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self._flat_grad[off:off + n].view_as(p)
+                self._offsets.append((off, n))
+                off += n
+
+    @property
+    def flat_grad(self):
+        self._materialize()
+        return self._flat_grad
+
+    def grad_slices(self):
+        """[(param, offset, numel)] in registration order (used to build all-reduce buckets)."""
+        self._materialize()
+        return [(p, o, n) for p, (o, n) in zip(self._params, self._offsets)]
+
+    def zero_grad(self, set_to_none=False):
+        self._materialize()
+        self._flat_grad.zero_()
+        for p, (off, n) in zip(self._params, self._offsets):
+            if p.grad is None or p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * off:
+                p.grad = self._flat_grad[off:off + n].view_as(p)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self._materialize()
+        # gradients written by autograd into fresh tensors (first backward) are folded into the flat buffer
+        for p, (off, n) in zip(self._params, self._offsets):
+            if p.grad is not None and p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * off:
+                self._flat_grad[off:off + n].view_as(p).copy_(p.grad)
+                p.grad = self._flat_grad[off:off + n].view_as(p)
+        self._step += 1
+        g = self.param_groups[0]
+        ops.k_adam(self._flat, self._flat_grad, self._m, self._v, self._step, g["lr"], g["betas"][0], g["betas"][1],
+                   g["eps"], self.grad_scale)
+        return None

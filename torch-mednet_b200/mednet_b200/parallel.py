@@ -1,0 +1,110 @@
+"""Patch-batch data parallelism: one process per GPU, bucketed gradient all-reduce overlapped with the
+backward pass (replaces what pytorch-lightning's DDP did for `Trainer(gpus=N)`, examples/train_seg.py:126).
+
+GroupNorm statistics are per sample (components.py:57), so the only exchange is the gradient all-reduce.
+Gradients live in ONE flat fp32 buffer (FusedAdam); buckets are contiguous slices of it laid out in
+backward-completion order (final_conv -> decoders -> encoders, i.e. reverse registration order).  A
+post-accumulate hook per parameter counts its bucket down; the last arrival launches an asynchronous
+`all_reduce(SUM)` of the bucket view on the process group's communication stream (NCCL over NVLink), which
+therefore overlaps the rest of backward.  The 1/world scaling is folded into the fused Adam kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients:
+    """Device-agnostic flat gradient buffer (used directly by the CPU/gloo tests; FusedAdam owns the GPU one)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices = []
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self.slices.append((p, off, n))
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+
+class BucketedAllReduce:
+    def __init__(self, grad_slices, flat_grad, bucket_bytes=25 << 20, process_group=None):
+        """grad_slices: [(param, offset, numel)] in registration order; flat_grad: the flat fp32 buffer."""
+        self.flat = flat_grad
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        cap = max(1, bucket_bytes // 4)
+        # buckets over the flat buffer from the END (backward order); each is one contiguous range
+        self.buckets = []          # [lo, hi, remaining, total]
+        self.bucket_of = {}
+        hi = lo = flat_grad.numel()
+        members = 0
+        for p, off, n in reversed(grad_slices):
+            if members and (hi - off) > cap:
+                self.buckets.append([lo, hi, members, members])
+                hi, members = lo, 0
+            lo = off
+            self.bucket_of[id(p)] = len(self.buckets)
+            members += 1
+        if members:
+            self.buckets.append([lo, hi, members, members])
+        self.handles = []
+        self.launch_order = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p, _, _ in grad_slices]
+
+    def _on_grad(self, param):
+        b = self.bucket_of[id(param)]
+        bucket = self.buckets[b]
+        bucket[2] -= 1
+        if bucket[2] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        lo, hi = self.buckets[b][0], self.buckets[b][1]
+        self.launch_order.append(b)
+        if self.world > 1:
+            self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Call after backward: flushes buckets whose parameters got no gradient, waits for the collectives
+        and re-arms the counters.  Returns the scale (1/world) the optimiser must apply."""
+        for b, bucket in enumerate(self.buckets):
+            if bucket[2] != 0:
+                self._launch(b)
+        for h in self.handles:
+            h.wait()
+        self.handles.clear()
+        self.launch_order.clear()
+        for bucket in self.buckets:
+            bucket[2] = bucket[3]
+        return 1.0 / self.world
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+def init_distributed(backend=None):
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun); returns (rank, local_rank, world)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, local, world

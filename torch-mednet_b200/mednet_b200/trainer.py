@@ -1,0 +1,69 @@
+"""A minimal training loop calling the PL-0.9 hooks of the task modules with the reference's Trainer
+arguments (examples/train_seg.py:126-132): gpus, max_epochs, default_root_dir, resume_from_checkpoint.
+pytorch-lightning itself is not in this image; device placement, data parallelism and checkpointing it
+provided are done here.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from .parallel import BucketedAllReduce, init_distributed
+
+
+def _to_device(batch, dev):
+    return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+class Trainer:
+    def __init__(self, gpus=1, max_epochs=1, default_root_dir=None, resume_from_checkpoint=None, logger=None,
+                 max_steps=None, log_every=10):
+        self.gpus, self.max_epochs, self.root = gpus, max_epochs, default_root_dir
+        self.resume, self.max_steps, self.log_every = resume_from_checkpoint, max_steps, log_every
+        self.history = []
+
+    def fit(self, model):
+        rank, local, world = init_distributed()
+        dev = torch.device("cuda", local)
+        model.to(dev)
+        opt = model.configure_optimizers()
+        start_epoch, step = 0, 0
+        if self.resume:
+            ckpt = torch.load(self.resume, map_location="cpu", weights_only=False)
+            model.load_state_dict(ckpt["state_dict"])
+            start_epoch, step = ckpt.get("epoch", 0), ckpt.get("global_step", 0)
+        reducer = None
+        if world > 1:
+            reducer = BucketedAllReduce(opt.grad_slices(), opt.flat_grad)
+        opt.zero_grad()
+        for epoch in range(start_epoch, self.max_epochs):
+            model.current_epoch = epoch
+            model.train()
+            for i, batch in enumerate(model.train_dataloader()):
+                out = model.training_step(_to_device(batch, dev), i)
+                out["loss"].backward()
+                if reducer is not None:
+                    opt.grad_scale = reducer.finish()
+                opt.step()
+                opt.zero_grad()
+                step += 1
+                model.global_step = step
+                if rank == 0 and step % self.log_every == 0:
+                    self.history.append({k: float(v) for k, v in out["log"].items()})
+                if self.max_steps and step >= self.max_steps:
+                    break
+            if getattr(model, "validation_dataset", None) is not None:
+                model.eval()
+                outs = []
+                with torch.no_grad():
+                    for i, batch in enumerate(model.val_dataloader()):
+                        outs.append(model.validation_step(_to_device(batch, dev), i))
+                if outs:
+                    self.history.append({k: float(v) for k, v in model.validation_epoch_end(outs)["log"].items()})
+            if rank == 0 and self.root:
+                os.makedirs(self.root, exist_ok=True)
+                model.save_checkpoint(os.path.join(self.root, f"epoch={epoch}.ckpt"), opt, epoch + 1, step)
+            if self.max_steps and step >= self.max_steps:
+                break
+        return model

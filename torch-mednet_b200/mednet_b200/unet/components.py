@@ -1,0 +1,289 @@
+"""Building blocks of the B200-native U-Nets: same constructor signatures, attribute names and
+``state_dict`` keys as midasmednet/unet/components.py, executed as fused CUDA kernels on NDHWC tensors.
+
+Reference map (file:line in /root/reference/midasmednet/unet/components.py):
+  create_conv / SingleConv ... :12-67, :70-90      order-string layer factory
+  DoubleConv ................. :93-133
+  ExtResNetBlock ............. :136-180
+  Encoder .................... :183-226
+  Decoder .................... :229-287
+
+Tensors crossing a module boundary are logically (N, C, D, H, W); internally they are channels-last-3d
+(NDHWC memory) in the compute dtype.  Any NCDHW tensor is accepted and converted on entry.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .. import ops
+
+_NONLIN = "rle"
+
+
+class ComputeConfig:
+    """Shared by every block of one network: compute dtype and convolution implementation."""
+
+    def __init__(self, dtype=torch.bfloat16, conv_impl="auto"):
+        self.dtype = dtype
+        self.conv_impl = conv_impl
+
+
+def to_ndhwc(x, cfg):
+    """(N,C,D,H,W) tensor -> NDHWC-contiguous (N,D,H,W,C) tensor in the compute dtype (view when possible)."""
+    if x.dim() != 5:
+        raise ValueError(f"expected a 5-D (N,C,D,H,W) tensor, got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("mednet_b200 runs on CUDA tensors only (no CPU fallback); move the module and inputs to a GPU")
+    v = x.permute(0, 2, 3, 4, 1)
+    if x.dtype == cfg.dtype and v.is_contiguous():
+        return v
+    return ops.ToChannelsLastFn.apply(x, cfg.dtype)
+
+
+def from_ndhwc(y):
+    return y.permute(0, 4, 1, 2, 3)
+
+
+class _ConvParams(nn.Module):
+    """Parameter holder with nn.Conv3d's default initialisation (kaiming_uniform(a=sqrt(5)))."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, bias, transposed=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size, self.transposed = in_channels, out_channels, kernel_size, transposed
+        k = kernel_size
+        shape = (in_channels, out_channels, k, k, k) if transposed else (out_channels, in_channels, k, k, k)
+        self.weight = nn.Parameter(torch.empty(shape))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.weight.shape[1] * self.kernel_size ** 3
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        kind = "ConvTranspose3d" if self.transposed else "Conv3d"
+        return f"{kind}({self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, bias={self.bias is not None})"
+
+
+class _GroupNormParams(nn.Module):
+    def __init__(self, num_groups, num_channels, eps=1e-5):
+        super().__init__()
+        self.num_groups, self.num_channels, self.eps = num_groups, num_channels, eps
+        self.weight = nn.Parameter(torch.ones(num_channels))
+        self.bias = nn.Parameter(torch.zeros(num_channels))
+
+    def extra_repr(self):
+        return f"GroupNorm({self.num_groups}, {self.num_channels}, eps={self.eps})"
+
+
+def conv3d(in_channels, out_channels, kernel_size, bias, padding=1):
+    if kernel_size != 3 or padding != 1:
+        raise NotImplementedError("mednet_b200 implements the 3x3x3 / padding 1 convolution of the reference nets")
+    return _ConvParams(in_channels, out_channels, kernel_size, bias)
+
+
+def create_conv(in_channels, out_channels, kernel_size, order, num_groups, padding=1):
+    """Same contract as components.py:12-67: list of (name, module) for one order string."""
+    assert 'c' in order, "Conv layer MUST be present"
+    assert order[0] not in 'rle', 'Non-linearity cannot be the first operation in the layer'
+    modules = []
+    for i, char in enumerate(order):
+        if char == 'r':
+            modules.append(('ReLU', nn.Identity()))
+        elif char == 'l':
+            modules.append(('LeakyReLU', nn.Identity()))
+        elif char == 'e':
+            modules.append(('ELU', nn.Identity()))
+        elif char == 'c':
+            bias = not ('g' in order or 'b' in order)
+            modules.append(('conv', conv3d(in_channels, out_channels, kernel_size, bias, padding=padding)))
+        elif char == 'g':
+            is_before_conv = i < order.index('c')
+            num_channels = in_channels if is_before_conv else out_channels
+            if num_channels < num_groups:
+                num_groups = 1
+            assert num_channels % num_groups == 0, f'Expected number of channels in input to be divisible by num_groups. num_channels={num_channels}, num_groups={num_groups}'
+            modules.append(('groupnorm', _GroupNormParams(num_groups, num_channels)))
+        elif char == 'b':
+            raise NotImplementedError("order letter 'b' (BatchNorm3d) is not selected by any reference model and is not built")
+        else:
+            raise ValueError(f"Unsupported layer type '{char}'. MUST be one of ['b', 'g', 'r', 'l', 'e', 'c']")
+    return modules
+
+
+class SingleConv(nn.Module):
+    """One order-string layer executed as fused kernels: 'g'+activation -> one GroupNorm kernel sequence,
+    'c'+activation -> conv with the activation in its epilogue."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order='crg', num_groups=8, padding=1, cfg=None):
+        super().__init__()
+        self.order = order
+        self.cfg = cfg if cfg is not None else ComputeConfig()
+        for name, module in create_conv(in_channels, out_channels, kernel_size, order, num_groups, padding=padding):
+            self.add_module(name, module)
+        # execution plan: list of (kind, fused_activation_code)
+        plan, i = [], 0
+        while i < len(order):
+            ch = order[i]
+            nxt = order[i + 1] if i + 1 < len(order) else ''
+            if ch in 'cg':
+                act = ops.ACT[nxt] if nxt and nxt in _NONLIN else 0
+                plan.append((ch, act))
+                i += 2 if act else 1
+            else:
+                plan.append(('a', ops.ACT[ch]))
+                i += 1
+        self._plan = plan
+
+    def run(self, x, residual=None, final_act=0):
+        """x: NDHWC tensor.  ``residual``/``final_act`` fuse `out += residual; act(out)` (components.py:177-178)
+        into the last kernel of the layer."""
+        last = len(self._plan) - 1
+        for i, (kind, act) in enumerate(self._plan):
+            fuse = (i == last) and (residual is not None or final_act)
+            if fuse and act:
+                raise RuntimeError("a residual join cannot follow a layer that already ends in a non-linearity")
+            if kind == 'c':
+                x = ops.Conv3x3Fn.apply(x, self.conv.weight, self.conv.bias, residual if fuse else None,
+                                        final_act if fuse else act, self.cfg.conv_impl)
+            elif kind == 'g':
+                gn = self.groupnorm
+                x = ops.GroupNormActFn.apply(x, gn.weight, gn.bias, gn.num_groups, final_act if fuse else act,
+                                             residual if fuse else None)
+            else:
+                x = ops.ActFn.apply(x, act)
+        return x
+
+    def forward(self, x):
+        return from_ndhwc(self.run(to_ndhwc(x, self.cfg)))
+
+
+class DoubleConv(nn.Module):
+    """components.py:93-133."""
+
+    def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order='crg', num_groups=8, cfg=None):
+        super().__init__()
+        self.cfg = cfg if cfg is not None else ComputeConfig()
+        if encoder:
+            conv1_in_channels = in_channels
+            conv1_out_channels = out_channels // 2
+            if conv1_out_channels < in_channels:
+                conv1_out_channels = in_channels
+            conv2_in_channels, conv2_out_channels = conv1_out_channels, out_channels
+        else:
+            conv1_in_channels, conv1_out_channels = in_channels, out_channels
+            conv2_in_channels, conv2_out_channels = out_channels, out_channels
+        self.add_module('SingleConv1', SingleConv(conv1_in_channels, conv1_out_channels, kernel_size, order, num_groups,
+                                                   cfg=self.cfg))
+        self.add_module('SingleConv2', SingleConv(conv2_in_channels, conv2_out_channels, kernel_size, order, num_groups,
+                                                   cfg=self.cfg))
+
+    def run(self, x):
+        return self.SingleConv2.run(self.SingleConv1.run(x))
+
+    def forward(self, x):
+        return from_ndhwc(self.run(to_ndhwc(x, self.cfg)))
+
+
+class ExtResNetBlock(nn.Module):
+    """components.py:136-180; the residual add and the trailing non-linearity are fused into conv3's
+    last kernel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order='cge', num_groups=8, cfg=None, **kwargs):
+        super().__init__()
+        self.cfg = cfg if cfg is not None else ComputeConfig()
+        self.conv1 = SingleConv(in_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups,
+                                cfg=self.cfg)
+        self.conv2 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups,
+                                cfg=self.cfg)
+        n_order = order
+        for c in 'rel':
+            n_order = n_order.replace(c, '')
+        self.conv3 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=n_order,
+                                num_groups=num_groups, cfg=self.cfg)
+        if 'l' in order:
+            self._act = ops.ACT['l']
+        elif 'e' in order:
+            self._act = ops.ACT['e']
+        else:
+            self._act = ops.ACT['r']
+        self.non_linearity = nn.Identity()
+
+    def run(self, x):
+        out = self.conv1.run(x)
+        residual = out
+        out = self.conv2.run(out)
+        return self.conv3.run(out, residual=residual, final_act=self._act)
+
+    def forward(self, x):
+        return from_ndhwc(self.run(to_ndhwc(x, self.cfg)))
+
+
+class _MaxPool(nn.Module):
+    def forward(self, x):
+        return ops.MaxPoolFn.apply(x)
+
+
+class Encoder(nn.Module):
+    """components.py:183-226."""
+
+    def __init__(self, in_channels, out_channels, conv_kernel_size=3, apply_pooling=True, pool_kernel_size=(2, 2, 2),
+                 pool_type='max', basic_module=DoubleConv, conv_layer_order='crg', num_groups=8, cfg=None):
+        super().__init__()
+        assert pool_type in ['max', 'avg']
+        self.cfg = cfg if cfg is not None else ComputeConfig()
+        if apply_pooling:
+            if pool_type != 'max' or tuple(pool_kernel_size) != (2, 2, 2):
+                raise NotImplementedError("only MaxPool3d(2) (the pooling every reference model selects) is built")
+            self.pooling = _MaxPool()
+        else:
+            self.pooling = None
+        self.basic_module = basic_module(in_channels, out_channels, encoder=True, kernel_size=conv_kernel_size,
+                                         order=conv_layer_order, num_groups=num_groups, cfg=self.cfg)
+
+    def run(self, x):
+        if self.pooling is not None:
+            x = self.pooling(x)
+        return self.basic_module.run(x)
+
+    def forward(self, x):
+        return from_ndhwc(self.run(to_ndhwc(x, self.cfg)))
+
+
+class Decoder(nn.Module):
+    """components.py:229-287: DoubleConv -> nearest upsample + concat (one kernel); otherwise learned
+    ConvTranspose3d + summation join (skip add fused into the transposed-conv epilogue)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, scale_factor=(2, 2, 2), basic_module=DoubleConv,
+                 conv_layer_order='crg', num_groups=8, cfg=None):
+        super().__init__()
+        self.cfg = cfg if cfg is not None else ComputeConfig()
+        if basic_module == DoubleConv:
+            self.upsample = None
+        else:
+            if kernel_size != 3 or tuple(scale_factor) != (2, 2, 2):
+                raise NotImplementedError("only ConvTranspose3d(k3, s2, p1, op1) is built")
+            self.upsample = _ConvParams(in_channels, out_channels, kernel_size, bias=True, transposed=True)
+            in_channels = out_channels
+        self.basic_module = basic_module(in_channels, out_channels, encoder=False, kernel_size=kernel_size,
+                                         order=conv_layer_order, num_groups=num_groups, cfg=self.cfg)
+
+    def run(self, encoder_features, x):
+        if self.upsample is None:
+            x = ops.UpsampleConcatFn.apply(encoder_features, x)
+        else:
+            x = ops.ConvTranspose3x3Fn.apply(x, self.upsample.weight, self.upsample.bias, encoder_features,
+                                             self.cfg.conv_impl)
+        return self.basic_module.run(x)
+
+    def forward(self, encoder_features, x):
+        return from_ndhwc(self.run(to_ndhwc(encoder_features, self.cfg), to_ndhwc(x, self.cfg)))
