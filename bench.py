@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the UNet3D training hot path (BASELINE.json metric: UNet3D train voxels/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg5|cfg1] [--impl reference]
+
+One step = one pass of the hot path over one synthetic batch: forward -> loss -> backward ->
+(bucketed all-reduce when N > 1) -> fused Adam.  Prints ONE JSON line (rank 0).
+
+  value      whole-job voxels/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public training_step API with HOST (pinned) batches: the H2D copy of
+             every step's inputs and the D2H read of the loss are inside the timed region
+  roofline   dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs of its launches divided
+             by their summed CUDA-event durations, against the measured dense bf16 peak
+  cpu_baseline  the oracle port (plain PyTorch fp32, oracle/) timed on the host cores on a bounded sample
+`--impl reference` times that CPU path alone with all host threads (the reference ships no GPU kernels of
+its own: every FLOP of it runs inside stock PyTorch).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "torch-mednet_b200"))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (arch, f_maps, classes, heatmaps, batch per GPU, patch edge, loss)
+    "cfg1": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=2, edge=64, loss="DICE",
+                 desc="UNet3D(1,2) f=64 4-level, batch 2, 64^3, Dice (examples/train_seg.py shape)"),
+    "cfg2": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=8, batch=4, edge=96, loss="DICE",
+                 desc="UNet3D landmark heatmap regression, 8 heatmaps + 2 classes, batch 4, 96^3"),
+    "cfg3": dict(arch="unet3d", f_maps=64, classes=4, heatmaps=0, batch=8, edge=128, loss="DICE",
+                 desc="UNet3D(1,4) f=64 4-level multi-class segmentation, batch 8 per GPU, 128^3, Dice"),
+    "cfg5": dict(arch="unet3d", f_maps=[32, 64, 128, 256, 512], classes=2, heatmaps=0, batch=2, edge=160, loss="DICE",
+                 desc="wide UNet3D f=[32..512] 5-level, batch 2 per GPU, 160^3, Dice"),
+    "tiny": dict(arch="unet3d", f_maps=[16, 32, 64], classes=2, heatmaps=0, batch=2, edge=32, loss="DICE",
+                 desc="smoke-sized UNet3D"),
+}
+
+
+def synthetic_batch(wl, seed, device, pin=False):
+    """MedDataset contract (dataset.py:332-346): data (B,1,S,S,S) f32; label (B,L+1,S,S,S) u8, class map last."""
+    g = torch.Generator().manual_seed(seed)
+    b, s = wl["batch"], wl["edge"]
+    data = torch.randn((b, 1, s, s, s), generator=g)
+    cls = torch.randint(0, wl["classes"], (b, 1, s, s, s), generator=g, dtype=torch.uint8)
+    if wl["heatmaps"]:
+        hm = torch.zeros((b, wl["heatmaps"], s, s, s), dtype=torch.uint8)
+        ax = torch.arange(s, dtype=torch.float32)
+        for n in range(b):
+            pts = torch.rand((wl["heatmaps"], 3), generator=g) * s
+            for l in range(wl["heatmaps"]):
+                r2 = ((ax[:, None, None] - pts[l, 0]) ** 2 + (ax[None, :, None] - pts[l, 1]) ** 2 +
+                      (ax[None, None, :] - pts[l, 2]) ** 2)
+                hm[n, l] = (255.0 * torch.exp(-r2 / 18.0)).to(torch.uint8)       # sigma = 3 voxels
+        label = torch.cat([hm, cls], dim=1)
+    else:
+        label = cls
+    batch = {"data": data, "label": label}
+    if pin:
+        return {k: v.pin_memory() for k, v in batch.items()}
+    return {k: v.to(device) for k, v in batch.items()}
+
+
+def hparams_for(wl):
+    ns = argparse.Namespace(in_channels=1, fmaps=wl["f_maps"], learning_rate=1e-3, num_workers=0, batch_size=wl["batch"])
+    if wl["heatmaps"]:
+        ns.out_channels = wl["heatmaps"] + wl["classes"]
+        ns.loss_class, ns.loss_class_weight = wl["loss"], [0.05] + [1.0] * (wl["classes"] - 1)
+        ns.loss_regression = "L2"
+        ns.loss_regression_weight = ([0.001, 0.015, 0.015, 0.015] + [0.001] * 8)[:wl["heatmaps"]]
+    else:
+        ns.out_channels = wl["classes"]
+        ns.loss, ns.loss_weight = wl["loss"], [0.05] + [1.0] * (wl["classes"] - 1)
+    return ns
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_voxels_per_s(wl, steps, warmup, edge=None, batch=None):
+    """Times the oracle port (forward + loss + backward + Adam) on the host cores; returns (voxels/s, info)."""
+    from oracle import steps as osteps
+    from oracle import unet as ounet
+    torch.set_num_threads(os.cpu_count() or 1)
+    edge = edge or wl["edge"]
+    batch = batch or wl["batch"]
+    sub = dict(wl, edge=edge, batch=batch)
+    out_ch = wl["classes"] + wl["heatmaps"]
+    sd = ounet.make_unet3d_state_dict(1, out_ch, wl["f_maps"])
+    b = synthetic_batch(sub, 0, "cpu")
+    kw = dict(f_maps=wl["f_maps"])
+    if wl["heatmaps"]:
+        hp = hparams_for(wl)
+        times, _ = osteps.time_training_steps("unet3d", sd, b, steps=steps, warmup=warmup, task="ldmk",
+                                              loss_class=hp.loss_class, loss_class_weight=hp.loss_class_weight,
+                                              loss_regression_weight=hp.loss_regression_weight, **kw)
+    else:
+        hp = hparams_for(wl)
+        times, _ = osteps.time_training_steps("unet3d", sd, b, steps=steps, warmup=warmup, task="seg", loss=hp.loss,
+                                              loss_weight=hp.loss_weight, **kw)
+    t = sum(times) / len(times)
+    vox = batch * edge ** 3
+    return vox / t, dict(seconds_per_step=t, sample=f"batch {batch} x {edge}^3 patch, {len(times)} timed step(s) after "
+                                                     f"{warmup} warm-up, fwd+loss+bwd+Adam, oracle port of the reference "
+                                                     f"(plain PyTorch fp32, {torch.get_num_threads()} threads)")
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    edge = min(wl["edge"], 64)
+    v, info = cpu_oracle_voxels_per_s(wl, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)), edge=edge, batch=1)
+    line = {"impl": "reference", "metric": "UNet3D train voxels/s", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "l2": "inputs larger than L2"},
+            "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": info["sample"]},
+            "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+    if args.warmup < 3:
+        args.warmup = 3                      # timing rule: >= 3 warm-up steps
+
+    import torch.distributed as dist
+    from mednet_b200 import ops
+    from mednet_b200.landmarks import LandmarkUNet3D
+    from mednet_b200.parallel import BucketedAllReduce, init_distributed
+    from mednet_b200.segmentation import SegmentationUNet3D
+
+    rank, local, world = init_distributed()
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    hp = hparams_for(wl)
+    cls = LandmarkUNet3D if wl["heatmaps"] else SegmentationUNet3D
+    model = cls(hp, conv_impl=args.conv_impl).to(dev)
+    opt = model.configure_optimizers()
+    reducer = BucketedAllReduce(opt.grad_slices(), opt.flat_grad) if world > 1 else None
+    opt.zero_grad()
+    batch_dev = synthetic_batch(wl, 1000 + rank, dev)
+    batch_host = synthetic_batch(wl, 1000 + rank, dev, pin=True)
+    h2d = sum(v.numel() * v.element_size() for v in batch_host.values())
+
+    def step(batch):
+        out = model.training_step(batch, 0)
+        out["loss"].backward()
+        if reducer is not None:
+            opt.grad_scale = reducer.finish()
+        opt.step()
+        opt.zero_grad()
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step(batch_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.conv_events = []                     # per-launch CUDA events of the dominant kernel (see ops.k_conv3)
+    launches0 = ops.launch_count
+    ms = timed(lambda: step(batch_dev), args.steps)
+    launches = ops.launch_count - launches0
+    conv_events, ops.conv_events = ops.conv_events, None
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}
+        return step(b).item()                # D2H read of the step's result (4 bytes) inside the timed region
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    vox_step = world * wl["batch"] * wl["edge"] ** 3
+    value = vox_step * args.steps / (ms * 1e-3)
+    e2e = vox_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0 if peaks else 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else \
+        "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    tc_flops = sum(f for f, _, _ in conv_events)
+    tc_ms = sum(a.elapsed_time(b) for _, a, b in conv_events)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 fprop+dgrad)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": None, "peak_source": peak_src, "launches_timed": len(conv_events),
+                "share_of_step": tc_ms / ms if ms else None}
+    line = {"metric": "UNet3D train voxels/s", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "per_gpu_batch": wl["batch"], "patch": wl["edge"],
+                       "parallelism": f"dp{world}", "l2": "inputs larger than L2 (activations are GBs per step)",
+                       "conv_impl": args.conv_impl, "tcgen05_variants": {str(k): v for k, v in ops.tcgen05_variants.items()
+                                                                           if k != "report"}},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        v, info = cpu_oracle_voxels_per_s(wl, steps=1, warmup=1, edge=min(wl["edge"], 64), batch=1)
+        line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": info["sample"]}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

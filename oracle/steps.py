@@ -77,7 +77,7 @@ def time_training_steps(kind, sd, batch, steps=3, warmup=1, lr=1e-3, task="seg",
             value = landmark_step(kind, leaf, batch, **step_kw)[0]
         value.backward()
         opt.step()
-        last = float(value)
+        last = float(value.detach())
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     return times, last

@@ -1,0 +1,167 @@
+"""Module- and step-level parity of the drop-in networks against the oracle and the golden vectors
+generated from the live reference (SURVEY.md section 4 (ii),(iii)).
+
+Gates (north star): logits relative error <= 1e-4 in the fp32 validation mode and <= 1e-2 in bf16;
+loss within 1e-3; per-parameter-tensor gradient cosine >= 0.999."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import state_dict_from
+from mednet_b200.landmarks import LandmarkNet
+from mednet_b200.predict import SlidingWindowPredictor
+from mednet_b200.segmentation import SegmentationUNet3D
+from mednet_b200.unet.loss import DiceLoss, dice_metric
+from mednet_b200.unet.model import ResidualUNet3D, UNet3D
+from oracle import steps as osteps
+from oracle import tiling as otiling
+from oracle import unet as ounet
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def cos(a, b):
+    return F.cosine_similarity(torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten(), dim=0).item()
+
+
+def test_unet3d_fp32_validation_mode_against_golden(golden):
+    g = golden("unet3d_small")
+    net = UNet3D(1, 2, False, f_maps=[8, 16, 32], compute_dtype=torch.float32).to(DEV)
+    net.load_state_dict(state_dict_from(g))
+    x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    logits = net(x)
+    assert logits.dtype == torch.float32 and logits.shape == (2, 2, 16, 16, 16)
+    assert relerr(logits.detach().cpu(), g["logits"]) < 1e-4
+    loss = DiceLoss(weight=torch.tensor([0.05, 1.0]))(logits, y)
+    assert abs(loss.item() - float(g["dice"])) < 1e-5
+    loss.backward()
+    for k, p in net.named_parameters():
+        assert cos(p.grad.cpu(), g["grad." + k]) > 0.9999, k
+        assert relerr(p.grad.cpu(), g["grad." + k]) < 2e-3, k
+    np.testing.assert_allclose(dice_metric(logits.detach(), y).cpu().numpy(), g["dice_metric"], rtol=1e-4)
+    odd = net(torch.from_numpy(g["x_odd"]).to(DEV))              # 13x14x15: pool floors, upsample restores
+    assert relerr(odd.detach().cpu(), g["logits_odd"]) < 1e-4
+    net.testing = True
+    assert relerr(net(x).detach().cpu(), g["probs"]) < 1e-4
+
+
+def test_unet3d_layer_orders_fp32(golden):
+    g = golden("unet3d_orders")
+    for order in ("crg", "cl", "gce"):
+        net = UNet3D(2, 3, False, f_maps=[8, 16], layer_order=order, compute_dtype=torch.float32).to(DEV)
+        net.load_state_dict(state_dict_from(g, f"{order}.sd."))
+        out = net(torch.from_numpy(g[f"{order}.x"]).to(DEV))
+        assert relerr(out.detach().cpu(), g[f"{order}.logits"]) < 1e-4, order
+
+
+def test_residual_unet_landmark_step_fp32_against_golden(golden):
+    g = golden("residual_small")
+    hp = argparse.Namespace(in_channels=1, out_channels=4, fmaps=[8, 16, 32], learning_rate=1e-3, num_workers=0,
+                            batch_size=2, loss_class="DICE", loss_class_weight=[0.05, 1.0], loss_regression="L2",
+                            loss_regression_weight=g["reg_w"].tolist())
+    net = LandmarkNet(hp, compute_dtype=torch.float32).to(DEV)
+    sd = state_dict_from(g)
+    sd["loss_class.weight"] = torch.tensor([0.05, 1.0])
+    net.load_state_dict(sd)
+    label = np.concatenate([g["heatmaps"], g["label"][:, None].astype(np.float32)], axis=1).astype(np.uint8)
+    batch = {"data": torch.from_numpy(g["x"]).to(DEV), "label": torch.from_numpy(label).to(DEV)}
+    out = net.training_step(batch, 0)
+    assert abs(out["loss"].item() - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    assert abs(float(out["log"]["class_loss"]) - float(g["class_loss"])) < 1e-4
+    assert abs(float(out["log"]["regression_loss"]) - float(g["regression_loss"])) < 1e-3 * abs(float(g["regression_loss"]))
+    assert relerr(net(batch["data"]).detach().cpu(), g["outputs"]) < 1e-4
+    out["loss"].backward()
+    for k, p in net.named_parameters():
+        assert cos(p.grad.cpu(), g["grad." + k]) > 0.9999, k
+    with pytest.raises(RuntimeError, match="must match the size"):
+        net(torch.zeros(1, 1, 10, 16, 16, device=DEV))          # sizes must divide 2**(levels-1) (components.py:284)
+
+
+@pytest.mark.parametrize("arch", ["unet3d", "residual"])
+def test_bf16_training_step_against_oracle(arch):
+    """bf16 production path (tensor-core convolutions) at channel counts the tcgen05 kernel takes."""
+    torch.manual_seed(0)
+    f_maps = [16, 32, 64]
+    if arch == "unet3d":
+        net = UNet3D(1, 3, False, f_maps=f_maps).to(DEV)
+        fwd = lambda sd, x: ounet.unet3d_forward(sd, x, f_maps=f_maps)
+    else:
+        net = ResidualUNet3D(1, 3, False, f_maps=f_maps).to(DEV)
+        fwd = lambda sd, x: ounet.residual_unet3d_forward(sd, x, f_maps=f_maps)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if "groupnorm" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    x = torch.randn(2, 1, 16, 32, 16)
+    y = torch.randint(0, 3, (2, 16, 32, 16))
+    w = torch.tensor([0.2, 1.0, 0.7])
+    sd = osteps.leaf_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()})
+    from oracle import loss as oloss
+    ref_logits = fwd(sd, x)
+    ref_loss = oloss.dice_loss(ref_logits, y, weight=w)
+    ref_grads = osteps.grads_of(ref_loss, sd)
+    logits = net(x.to(DEV))
+    loss = DiceLoss(weight=w)(logits, y.to(DEV))
+    loss.backward()
+    assert relerr(logits.detach().cpu(), ref_logits.detach()) < 1e-2
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    for k, p in net.named_parameters():
+        assert cos(p.grad.cpu(), ref_grads[k]) > 0.999, (k, cos(p.grad.cpu(), ref_grads[k]))
+
+
+def test_segmentation_training_loop_decreases_loss_and_checkpoint_roundtrip(tmp_path):
+    torch.manual_seed(0)
+    hp = argparse.Namespace(in_channels=1, out_channels=2, fmaps=[16, 32], learning_rate=3e-3, num_workers=0,
+                            batch_size=2, loss="CE", loss_weight=[0.3, 0.7])
+    net = SegmentationUNet3D(hp).to(DEV)
+    opt = net.configure_optimizers()
+    x = torch.randn(2, 1, 16, 16, 16, device=DEV)
+    lab = (x[:, 0] > 0).to(torch.uint8)[:, None]                 # learnable target
+    batch = {"data": x, "label": lab}
+    losses = []
+    for i in range(12):
+        out = net.training_step(batch, i)
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(float(out["log"]["train_loss"]))
+    assert losses[-1] < 0.7 * losses[0], losses
+    val = net.validation_step(batch, 0)
+    assert set(val) == {"val_loss", "val_dice0", "val_dice1"}
+    path = str(tmp_path / "m.ckpt")
+    net.save_checkpoint(path, opt, 1, 12)
+    net2 = SegmentationUNet3D.load_from_checkpoint(path).to(DEV)
+    net2.freeze()
+    assert torch.equal(net2(x), net(x).detach())
+
+
+def test_sliding_window_predictor_matches_reference_loop():
+    torch.manual_seed(1)
+    L, K = 2, 3
+    net = UNet3D(1, L + K, False, f_maps=[8, 16], compute_dtype=torch.float32).to(DEV)
+    with torch.no_grad():
+        net.final_conv.weight.mul_(40.0)                         # spread heatmap logits over the uint8 range
+    net.eval()
+    vol = np.random.default_rng(0).standard_normal((1, 41, 30, 37)).astype(np.float32)
+
+    def forward_fn(batch):
+        with torch.no_grad():
+            return net(torch.from_numpy(batch).to(DEV)).cpu().numpy()
+
+    want = otiling.sliding_window_predict(vol, forward_fn, [16] * 3, [3] * 3, L, L + 1, batch_size=3)
+    got = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=5)(vol).cpu().numpy()
+    mism = (got != want).mean()
+    assert mism < 1e-4, mism                                     # identical kernels; only batch-shape independent
+    # tile sharding: two "ranks" cover disjoint regions whose union is the full result
+    a = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=0, world=2)(vol, combine=False)
+    b = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=1, world=2)(vol, combine=False)
+    assert np.array_equal(torch.maximum(a, b).cpu().numpy(), got)

@@ -1,0 +1,83 @@
+"""tcgen05/TMEM implicit-GEMM convolution: descriptor calibration probe and parity against F.conv3d
+(CPU fp32 on bf16-rounded operands).  Tolerance: relative error <= 1e-2 (north star, bf16 mode); with
+fp32 accumulation and exact bf16 products the observed error is set by the bf16 output rounding (~3e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mednet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def relerr(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_probe_finds_a_working_descriptor_variant():
+    v = ops.calibrate_tcgen05(force=True)
+    rep = v["report"]
+    print({k: val for k, val in rep.items()})
+    for rb in (128, 64, 32):
+        assert rep[f"rb{rb}.aligned.bo0"], "canonical aligned K-major descriptor must address correctly"
+        assert v[rb]["enabled"] == 1, f"no shifted-window variant works for {rb}-byte rows: {rep}"
+
+
+CASES = [
+    # N, K(Cin), Nout, (D,H,W)
+    (1, 64, 64, (2, 16, 8)),        # exactly one brick, one chunk
+    (2, 64, 64, (5, 20, 12)),       # ragged tiles in all three axes, odd depth
+    (1, 32, 32, (4, 16, 16)),       # 64-byte rows (SW64)
+    (1, 16, 32, (3, 9, 9)),         # 32-byte rows (SW32)
+    (1, 96, 32, (4, 16, 8)),        # 3 chunks of 32
+    (1, 192, 64, (4, 16, 16)),      # decoder shape class 192 -> 64 (3 chunks of 64)
+    (1, 64, 128, (4, 16, 8)),
+    (1, 128, 256, (2, 16, 8)),      # Ntile = 256: single accumulator stage
+    (1, 64, 512, (2, 8, 8)),        # Nout split into two N tiles
+    (3, 64, 48, (6, 18, 10)),       # N not a power of two
+]
+
+
+@pytest.mark.parametrize("n,k,nout,shape", CASES)
+def test_conv3_tcgen05_matches_conv3d(n, k, nout, shape):
+    torch.manual_seed(k + nout)
+    x = torch.randn(n, k, *shape).bfloat16()
+    w = (torch.randn(nout, k, 3, 3, 3) / (27 * k) ** 0.5).bfloat16()
+    b = torch.randn(nout)
+    ref = F.relu(F.conv3d(x.float(), w.float(), b, padding=1))
+    xg = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    impl = ops.conv_select_impl(xg.shape, shape, k, nout, torch.bfloat16, 0, "tcgen05", xg.data_ptr())
+    assert impl == 2
+    y = ops.Conv3x3Fn.apply(xg, w.float().to(DEV), b.to(DEV), None, 1, "tcgen05")
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 4, 1, 2, 3).cpu()
+    assert relerr(got, ref) < 5e-3
+    assert (got - ref).abs().max() < 0.05
+
+
+def test_conv3_tcgen05_dgrad_and_epilogue_addend():
+    torch.manual_seed(7)
+    n, cin, cout, shape = 2, 64, 128, (4, 16, 8)
+    x = torch.randn(n, cin, *shape).bfloat16().float().requires_grad_()
+    w = (torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5).bfloat16().float().requires_grad_()
+    add = torch.randn(n, cout, *shape).bfloat16().float()
+    ref = F.elu(F.conv3d(x, w, None, padding=1) + add)
+    g = torch.randn_like(ref).bfloat16().float()
+    ref.backward(g)
+    xg = x.detach().permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16).requires_grad_()
+    wg = w.detach().to(DEV).requires_grad_()
+    ag = add.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    y = ops.Conv3x3Fn.apply(xg, wg, None, ag, 3, "tcgen05")
+    y.backward(g.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16))
+    assert relerr(y.detach().float().permute(0, 4, 1, 2, 3).cpu(), ref.detach()) < 5e-3
+    assert relerr(xg.grad.float().permute(0, 4, 1, 2, 3).cpu(), x.grad) < 1e-2
+    cos = F.cosine_similarity(wg.grad.flatten().cpu(), w.grad.flatten(), dim=0).item()
+    assert cos > 0.999
+
+
+def test_auto_selects_tensor_cores_for_bf16_and_simt_for_fp32():
+    x = torch.zeros(1, 4, 16, 8, 64, device=DEV, dtype=torch.bfloat16)
+    assert ops.conv_select_impl(x.shape, (4, 16, 8), 64, 64, torch.bfloat16, 0, "auto", x.data_ptr()) == 2
+    assert ops.conv_select_impl(x.shape, (4, 16, 8), 64, 64, torch.float32, 0, "auto", x.data_ptr()) == 1
+    assert ops.conv_select_impl((1, 4, 16, 8, 1), (4, 16, 8), 1, 32, torch.bfloat16, 0, "auto") == 1   # Cin = 1

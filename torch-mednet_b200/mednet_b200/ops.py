@@ -17,6 +17,7 @@ _DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2, torch.int64: 3}
 IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
 
 launch_count = 0          # kernels-API calls issued (bench.py reads it for `gpu_launches`)
+conv_events = None        # when a list: (algorithmic FLOPs, start event, end event) per tcgen05 conv launch
 
 
 def _dt(t):
@@ -174,7 +175,14 @@ def k_conv3(x, w_packed, nout, out_sp, gather, impl_id, bias=None, addend=None, 
              Di=di, Hi=hi, Wi=wi, Do=out_sp[0], Ho=out_sp[1], Wo=out_sp[2], K=k, Nout=nout, dtype=_dt(x), act=act,
              act_param=ACT_PARAM[act], gather=gather, impl=impl_id)
     ws = _ws(256, x.device)
+    timing = conv_events is not None and impl_id == 2
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().mednet_conv3d_fprop(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_fprop")
+    if timing:
+        e1.record()
+        conv_events.append((2.0 * n * out_sp[0] * out_sp[1] * out_sp[2] * k * nout * 27, e0, e1))
     _count()
     return y
 
