@@ -510,7 +510,7 @@ class Conv3x3Fn(torch.autograd.Function):
             wp = k_pack_weights(weight, cin, cout, dpre.dtype, 3 if impl_id == 2 else 1)
             dx = k_conv3(dpre, wp, cin, sp, 0, impl_id)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = k_wgrad(dpre, x, 0, ctx.impl, want_bias=ctx.has_bias)
+            dw, db = k_wgrad(dpre, x, 0, "simt" if ctx.impl == "simt" else "auto", want_bias=ctx.has_bias)
         return dx, dw, db, (dpre if ctx.has_addend else None), None, None
 
 
