@@ -377,6 +377,23 @@ int mednet_tcgen05_probe(const void* a_bf16 /* [rows][row_bytes/2] */, int32_t r
                          int32_t row_shift, int32_t sbo_bytes, int32_t base_offset_mode,
                          float* out /* [128][row_bytes/2] */, mednet_stream_t stream);
 
+/* UMMA descriptor laboratory (diagnostics / calibration, tests/test_tcgen05_gpu.py): a [rows][row_bytes] image of
+ * 16-bit elements is written to shared memory by TMA (swizzle = row_bytes), then `ksteps` tcgen05.mma
+ * (M x N x 16, fp32 accumulate) are issued with the shared-memory descriptors described here -- byte offsets into
+ * the image, leading/stride byte offsets, K- or MN-major, per-step address advance, operand formats
+ * (0 = f16, 1 = bf16) -- and the 128 x N accumulator is returned. */
+typedef struct {
+  const void* g; float* out;
+  int32_t rows, row_bytes, M, N, ksteps;
+  int32_t a_off, a_lbo, a_sbo, a_mn_major, a_kstep;
+  int32_t b_off, b_lbo, b_sbo, b_mn_major, b_kstep;
+  int32_t a_fmt, b_fmt;
+  int32_t iters;          /* repeat the k-step sequence (timing); 0 = once */
+  int64_t* cycles;        /* optional device scalar: SM clocks from first issue to completion */
+  int32_t nacc;           /* timing: rotate over this many independent accumulators (0 = 1); out = the first */
+} mednet_umma_lab_params;
+int mednet_umma_lab(const mednet_umma_lab_params* p, mednet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,3 +81,73 @@ def test_auto_selects_tensor_cores_for_bf16_and_simt_for_fp32():
     assert ops.conv_select_impl(x.shape, (4, 16, 8), 64, 64, torch.bfloat16, 0, "auto", x.data_ptr()) == 2
     assert ops.conv_select_impl(x.shape, (4, 16, 8), 64, 64, torch.float32, 0, "auto", x.data_ptr()) == 1
     assert ops.conv_select_impl((1, 4, 16, 8, 1), (4, 16, 8), 1, 32, torch.bfloat16, 0, "auto") == 1   # Cin = 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core weight gradient (csrc/wgrad_tcgen05.cu): MN-major operands, kw-chained taps, split-K partials
+# ---------------------------------------------------------------------------------------------------------
+WGRAD_CASES = [
+    # N, Cin, Cout, (D,H,W)
+    (1, 32, 64, (2, 16, 8)),        # U = dY (64 ch, second M atom zero-filled), one brick
+    (1, 64, 64, (4, 16, 16)),
+    (2, 64, 128, (5, 20, 12)),      # ragged bricks in all axes, odd depth; U = dY 128
+    (1, 192, 64, (4, 16, 8)),       # U = X (192 = 128 + 64): mirrored taps, partially filled second U tile
+    (1, 128, 128, (3, 9, 9)),
+    (1, 384, 128, (2, 8, 8)),       # U = X, 3 U tiles, 4 S chunks
+    (2, 256, 512, (1, 5, 7)),       # depth 1 (TD = 1), U = dY 512
+    (1, 64, 96, (2, 16, 8)),        # S = X 64 ch, U = dY 96?? -> 96 % 64 != 0: must be refused (SIMT)
+]
+
+
+def _wgrad_ref(x, dy):
+    """dW of y = conv3d(x, w, padding=1) for upstream gradient dy (fp64 on the CPU)."""
+    cin, cout = x.shape[1], dy.shape[1]
+    w = torch.zeros(cout, cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), w, None, padding=1).backward(dy.double())
+    return w.grad
+
+
+@pytest.mark.parametrize("n,cin,cout,shape", WGRAD_CASES)
+def test_wgrad_tcgen05_exact_on_integer_data(n, cin, cout, shape):
+    """Small-integer operands: every product and every fp32 partial sum is exact, so the tensor-core result must
+    equal the reference BIT FOR BIT whatever the summation order (catches any mis-addressed tap/voxel/channel)."""
+    torch.manual_seed(cin * 7 + cout)
+    x = torch.randint(-3, 4, (n, cin) + shape).float()
+    dy = torch.randint(-3, 4, (n, cout) + shape).float()
+    xg = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    dg = dy.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    p = ops.wgrad_params(dg, xg, 0, "auto")
+    impl = ops.lib().mednet_conv3d_wgrad_select_impl(ops._abi.C.byref(p))
+    cu, cs = (cin, cout) if cin > cout else (cout, cin)       # U = the operand with more channels, S = the other
+    if cu % 64 != 0 or cs % 32 != 0:
+        assert impl == 1                                      # refused by the tensor-core planner -> CUDA-core kernel
+        return
+    assert impl == 2, "bf16 wgrad with 64/32-aligned channels must run on the tensor cores"
+    dw, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
+    torch.cuda.synchronize()
+    ref = _wgrad_ref(x, dy)
+    assert torch.equal(dw.cpu().double(), ref)
+
+
+def test_wgrad_tcgen05_random_data_and_bias():
+    torch.manual_seed(3)
+    n, cin, cout, shape = 2, 64, 128, (6, 18, 10)
+    x = torch.randn(n, cin, *shape).bfloat16().float()
+    dy = torch.randn(n, cout, *shape).bfloat16().float()
+    xg = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    dg = dy.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    dw, db = ops.k_wgrad(dg, xg, 0, "tcgen05", want_bias=True)
+    ref = _wgrad_ref(x, dy).float()
+    assert relerr(dw.cpu(), ref) < 1e-5          # bf16 products are exact in fp32; only the summation order differs
+    assert relerr(db.cpu(), dy.sum(dim=(0, 2, 3, 4))) < 1e-5
+    dw_simt, _ = ops.k_wgrad(dg, xg, 0, "simt")
+    assert relerr(dw.cpu(), dw_simt.cpu()) < 1e-5
+
+
+def test_wgrad_tcgen05_is_deterministic():
+    torch.manual_seed(5)
+    xg = torch.randn(2, 8, 16, 16, 64, device=DEV).to(torch.bfloat16)
+    dg = torch.randn(2, 8, 16, 16, 64, device=DEV).to(torch.bfloat16)
+    a, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
+    b, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
+    assert torch.equal(a, b)

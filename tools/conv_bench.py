@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Per-layer micro-benchmark of the 3x3x3 convolution kernels (fprop / dgrad / wgrad) on the UNet3D layer shapes.
+GPU only.  Prints one JSON line per (layer, pass): algorithmic TFLOP/s from CUDA events, median of `reps`."""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "torch-mednet_b200"))
+from mednet_b200 import ops  # noqa: E402
+
+# (Cin, Cout, spatial divisor) of UNet3D f=64
+LAYERS = [(32, 64, 1), (64, 64, 2), (64, 128, 2), (128, 128, 4), (128, 256, 4), (256, 256, 8), (256, 512, 8),
+          (768, 256, 4), (256, 256, 4), (384, 128, 2), (128, 128, 2), (192, 64, 1), (64, 64, 1)]
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--edge", type=int, default=128)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--passes", default="fprop,wgrad")
+    ap.add_argument("--wgrad-impl", default="auto")
+    a = ap.parse_args()
+    dev = "cuda"
+    ops.calibrate_tcgen05()
+    for cin, cout, div in LAYERS:
+        s = a.edge // div
+        x = torch.randn(a.batch, s, s, s, cin, device=dev).to(torch.bfloat16)
+        dy = torch.randn(a.batch, s, s, s, cout, device=dev).to(torch.bfloat16)
+        w = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.05
+        flops = 2.0 * a.batch * s ** 3 * cin * cout * 27
+        if "fprop" in a.passes:
+            impl = ops.conv_select_impl(x.shape, (s, s, s), cin, cout, x.dtype, 0, "auto", x.data_ptr())
+            wp = ops.k_pack_weights(w, cin, cout, x.dtype, 2 if impl == 2 else 0)
+            ms = timed(lambda: ops.k_conv3(x, wp, cout, (s, s, s), 0, impl), a.reps)
+            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="fprop", impl=impl, ms=ms, tflops=flops / ms / 1e9)))
+        if "wgrad" in a.passes:
+            ms = timed(lambda: ops.k_wgrad(dy, x, 0, a.wgrad_impl), a.reps)
+            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9)))
+        del x, dy
+
+
+if __name__ == "__main__":
+    main()

@@ -152,17 +152,29 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
+    // The issuing thread is a serial instruction stream: every instruction between two tcgen05.mma costs
+    // ~4-5 clk of dependent latency, and an M=128 MMA only occupies the tensor pipe for N/2 clk (32 clk at
+    // N=64).  So the descriptors are built ONCE; per MMA only the 32-bit address word is advanced by
+    // register-resident offsets (measured: 111 clk/MMA with per-MMA descriptor construction, 55 clk lean).
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.Ntile, 0, 0);
       const uint32_t layout = p.RB == 128 ? tc::SWZ_128B : (p.RB == 64 ? tc::SWZ_64B : tc::SWZ_32B);
-      const uint32_t a_sbo = (uint32_t)(p.pitch * p.RB), b_sbo = (uint32_t)(8 * p.RB);
-      const uint32_t a_u32 = tc::smem_u32(a_base), b_u32 = tc::smem_u32(b_base);
+      const uint64_t da_base = tc::make_smem_desc(tc::smem_u32(a_base), 16, (uint32_t)(p.pitch * p.RB), 0, layout);
+      const uint64_t db_base = tc::make_smem_desc(tc::smem_u32(b_base), 16, (uint32_t)(8 * p.RB), 0, layout);
+      const uint32_t a_hi = (uint32_t)(da_base >> 32), b_hi = (uint32_t)(db_base >> 32);
+      const uint32_t a_lo0 = (uint32_t)da_base, b_lo0 = (uint32_t)db_base;
+      const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4, b16 = (uint32_t)p.b_bytes >> 4;
+      uint32_t tapoff[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) tapoff[i] = (uint32_t)(((i / 3) * p.pitch + (i % 3)) * p.RB) >> 4;
       const int ksteps = p.RB / 32;
       uint32_t ait = 0, bit = 0, tcount = 0;
+      uint32_t bst = 0, bph = 0;                       // B ring position (stage, parity) without div/mod
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
         tc::mbar_wait(&acc_empty[as], aph ^ 1u);
         tc::tc_fence_after();
+        const uint32_t d_tile = tmem_base + as * (uint32_t)(p.TD * p.Ntile);
         for (int c = 0; c < p.nchunks; ++c, ++ait) {
           for (int kd = 0; kd < 3; ++kd) {
             if (kd == 0) {
@@ -171,24 +183,32 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               tc::mbar_wait(&a_full[p.TD - 1 + kd], ait & 1u);
             }
             tc::tc_fence_after();
-            for (int khw = 0; khw < 9; ++khw, ++bit) {
-              const int kh = khw / 3, kw = khw - kh * 3;
-              const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
-              tc::mbar_wait(&b_full[st], ph);
+            const uint32_t a_kd = a_lo0 + (uint32_t)kd * plane16;
+#pragma unroll
+            for (int khw = 0; khw < 9; ++khw) {
+              tc::mbar_wait(&b_full[bst], bph);
               tc::tc_fence_after();
-              const uint32_t b_addr = b_u32 + st * (uint32_t)p.b_bytes;
+              const uint32_t b_lo = b_lo0 + bst * b16;
+              uint32_t a_lo = a_kd + tapoff[khw];
+              uint32_t d_tmem = d_tile;
+              const uint32_t first = (uint32_t)(c | kd | khw);
               for (int dz = 0; dz < p.TD; ++dz) {
-                const uint32_t a_addr =
-                    a_u32 + (uint32_t)(dz + kd) * (uint32_t)p.plane_bytes + (uint32_t)((kh * p.pitch + kw) * p.RB);
-                const uint32_t bo = p.bo_mode == 0 ? 0u : (p.bo_mode == 1 ? ((a_addr >> 7) & 7u) : ((a_addr / (uint32_t)p.RB) & 7u));
-                const uint32_t d_tmem = tmem_base + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t da = tc::make_smem_desc(a_addr + k * 32, 16, a_sbo, bo, layout);
-                  const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, b_sbo, 0, layout);
-                  tc::umma_bf16(d_tmem, da, db, idesc, (c | kd | khw | k) != 0 ? 1u : 0u);
+                if (ksteps == 4) {
+                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                  tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  tc::umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                  tc::umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                } else if (ksteps == 2) {
+                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                  tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                } else {
+                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
                 }
+                a_lo += plane16;
+                d_tmem += (uint32_t)p.Ntile;
               }
-              tc::umma_commit(&b_empty[st]);
+              tc::umma_commit(&b_empty[bst]);
+              if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
             }
             // planes whose last tap phase is this kd can be refilled for the next chunk
             if (kd < 2) {
@@ -200,6 +220,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tc::umma_commit(&acc_full[as]);
       }
+      (void)bit;
     }
   } else {
     // ===================== epilogue =====================
@@ -276,9 +297,10 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   p.Ntile = pick_ntile(q->Nout);
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
   p.nchunks = q->K / (p.RB / 2);
-  p.TD = q->Do >= 2 ? 2 : 1;
+  // more planes per brick = fewer halo re-reads and weight-tile loads per voxel; TMEM holds TD * Ntile columns per stage
+  p.TD = (p.Ntile <= 64 && q->Do >= 4) ? 4 : (q->Do >= 2 ? 2 : 1);
   const int rc = rb_class(p.RB);
-  if (!g_enabled[rc]) return false;
+  if (!g_enabled[rc] || g_base_offset_mode[rc] != 0) return false;   // the kernel issues base_offset = 0 descriptors
   p.per_row = g_dense_halo[rc] ? 0 : 1;
   p.pitch = g_dense_halo[rc] ? HALO_W : 16;
   p.bo_mode = g_base_offset_mode[rc];
@@ -357,11 +379,6 @@ int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }
-
-// tensor-core weight gradient: not built yet -> the dispatcher routes wgrad to the SIMT kernel
-bool tc_wgrad_supported(const mednet_wgrad_params*) { return false; }
-size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params*) { return 0; }
-int tc_wgrad(const mednet_wgrad_params*, void*, cudaStream_t) { return MEDNET_EUNSUPPORTED; }
 
 // ------------------------------------------------------------------------------------------------
 // descriptor probe: D = A_window * I with A written by TMA (swizzle = row bytes), B = identity written

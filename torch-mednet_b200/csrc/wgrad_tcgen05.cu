@@ -1,0 +1,317 @@
+// Weight gradient of the 3x3x3 convolution on the 5th-generation tensor cores.
+// ref: the autograd backward of nn.Conv3d at midasmednet/unet/components.py:8-9:
+//      dW[co][ci][kd][kh][kw] = sum_v dY[v][co] * X[v + (kd-1, kh-1, kw-1)][ci]   (zero outside the volume)
+//
+// GEMM view.  The reduction (K) runs over VOXELS, so with NDHWC activations both operands are "MN-major"
+// (channels contiguous, K strided): a TMA box of [voxels][channels] lands in shared memory exactly in the
+// canonical MN-major swizzled layout (one voxel = one row), verified on the device by csrc/umma_lab.cu.
+//   U  "unshifted" operand (A, M = 128 channels = 2 atoms of 64): a brick of TD x 16 x 8 voxels of the tensor
+//      with MORE channels (dY or X).  Channels past the tensor end are zero-filled by TMA.
+//   S  "shifted" operand (B): the (TD+2) x 18 x 10 HALO of the same brick of the OTHER tensor, 32 channels per
+//      CTA, staged once.  The 27 taps are 27 shifted windows of that halo (descriptor start address only).
+//      The three kw taps of one (kd, kh) are three windows one voxel row apart: the descriptor's
+//      leading-dimension stride chains them into ONE instruction with N = 3 x 32 = 96.
+//   D  one 128 x 96 fp32 accumulator per (kd, kh) group in TMEM; a CTA owns 5 (or 4) of the 9 groups
+//      ("role"), 480 of the 512 TMEM columns, and accumulates over all the bricks it is given.
+// Which tensor is U: the one with more channels.  With U = X, S = dY the sum is taken over X voxels u and
+// the window offsets are mirrored:  dW[co][ci][k] = sum_u X[u][ci] * dY[u - (k-1)][co].
+// Work decomposition: (U tile of 128 ch) x (S chunk of 32 ch) x (2 roles) x (split over bricks); every CTA
+// writes one fp32 partial [128][480] and a second kernel sums the splits in a fixed order (deterministic)
+// into the PyTorch (Cout, Cin, 3, 3, 3) layout.
+// Cost model (measured): an M=128, N=96, K=16 MMA costs max(N/2, (4 KB + 32 N)/128) = 56 clk for
+// 48 clk of math -> 86 % tensor-pipe ceiling; staging is (TD*32 + (TD+2)*11.25) KB per TD*16*5 MMAs.
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_impl.h"
+#include "tc_common.cuh"
+
+namespace mednet {
+
+namespace {
+
+constexpr int WG_THREADS = 192;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue
+constexpr int BR_H = 16, BR_W = 8;       // brick (h, w); depth TD
+constexpr int HL_H = 18, HL_W = 10;      // halo plane
+constexpr int CS = 32;                   // S channels per CTA (64-byte rows, SWIZZLE_64B)
+constexpr int NCOLS = 3 * CS;            // N of one MMA (three chained kw taps)
+constexpr int GROUPS0 = 5;               // (kd,kh) groups owned by role 0; role 1 owns the other 4
+constexpr int PART_COLS = GROUPS0 * NCOLS;   // 480 columns per partial row
+constexpr int STAGES = 2;
+
+struct WgArgs {
+  int N, D, H, W;
+  int CU, CSn;                 // channels of U and S
+  int TD;
+  int tiles_d, tiles_h, tiles_w;
+  int64_t bricks;              // N * tiles_d * tiles_h * tiles_w
+  int u_tiles, s_chunks, ksplit;
+  int64_t bricks_per_split;
+  float* partial;              // [worktype][ksplit][128][PART_COLS]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const WgArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int u_atom_bytes = p.TD * 128 * 128;                       // one 64-channel atom of the brick
+  const int u_bytes = 2 * u_atom_bytes;
+  const int s_bytes_raw = (p.TD + 2) * HL_H * HL_W * (2 * CS);
+  const int s_bytes = (s_bytes_raw + 1023) & ~1023;
+  const int stage_bytes = u_bytes + s_bytes;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)STAGES * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* done = bars + 2 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item of this CTA
+  int wt = blockIdx.x / p.ksplit;
+  const int ks = blockIdx.x - wt * p.ksplit;
+  const int role = wt & 1; wt >>= 1;
+  const int sc = wt % p.s_chunks;
+  const int ut = wt / p.s_chunks;
+  const int ngroups = role == 0 ? GROUPS0 : 9 - GROUPS0;
+  const int g0 = role == 0 ? 0 : GROUPS0;
+  const int64_t b_begin = (int64_t)ks * p.bricks_per_split;
+  int64_t b_end = b_begin + p.bricks_per_split;
+  if (b_end > p.bricks) b_end = p.bricks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+    tc::tma_prefetch_desc(&map_u);
+    tc::tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512u);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      uint32_t it = 0;
+      for (int64_t b = b_begin; b < b_end; ++b, ++it) {
+        const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+        int64_t t = b;
+        const int w0 = (int)(t % p.tiles_w) * BR_W; t /= p.tiles_w;
+        const int h0 = (int)(t % p.tiles_h) * BR_H; t /= p.tiles_h;
+        const int d0 = (int)(t % p.tiles_d) * p.TD;
+        const int n = (int)(t / p.tiles_d);
+        tc::mbar_wait(&empty[st], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&full[st], (uint32_t)(u_bytes + s_bytes_raw));
+        uint8_t* dst = smem + (size_t)st * stage_bytes;
+        tc::tma_load_5d(dst, &map_u, &full[st], ut * 128, w0, h0, d0, n);
+        tc::tma_load_5d(dst + u_atom_bytes, &map_u, &full[st], ut * 128 + 64, w0, h0, d0, n);
+        tc::tma_load_5d(dst + u_bytes, &map_s, &full[st], sc * CS, w0 - 1, h0 - 1, d0 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_16(128, NCOLS, 1, 1, 1, 1);
+      // per-group window offset inside the halo, in descriptor units (16 bytes)
+      uint32_t goff[GROUPS0];
+#pragma unroll
+      for (int g = 0; g < GROUPS0; ++g) {
+        const int gg = g0 + (g < ngroups ? g : 0);
+        const int gd = gg / 3, gh = gg - gd * 3;
+        goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W) * (2 * CS)) >> 4;
+      }
+      const uint32_t s_base = tc::smem_u32(smem);
+      uint32_t it = 0;
+      for (int64_t b = b_begin; b < b_end; ++b, ++it) {
+        const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+        tc::mbar_wait(&full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t u_addr = s_base + st * (uint32_t)stage_bytes;
+        // A: MN-major, 128-byte rows, atoms u_atom_bytes apart, 8-row groups 1024 B apart
+        const uint64_t da0 = tc::make_smem_desc(u_addr, (uint32_t)u_atom_bytes, 1024u, 0, tc::SWZ_128B);
+        // B: MN-major, 64-byte rows, three chained windows one row (64 B) apart, 8-row groups = next halo row
+        const uint64_t db0 = tc::make_smem_desc(u_addr + (uint32_t)u_bytes, (uint32_t)(2 * CS), (uint32_t)(HL_W * 2 * CS), 0,
+                                                tc::SWZ_64B);
+        uint32_t acc = it != 0 ? 1u : 0u;
+        for (int dz = 0; dz < p.TD; ++dz) {
+          const uint64_t da_z = da0 + (uint64_t)((dz * 128 * 128) >> 4);
+          const uint64_t db_z = db0 + (uint64_t)((dz * HL_H * HL_W * 2 * CS) >> 4);
+#pragma unroll
+          for (int hp = 0; hp < 8; ++hp) {
+            const uint64_t da = da_z + (uint64_t)((hp * 16 * 128) >> 4);
+            const uint64_t db = db_z + (uint64_t)((hp * 2 * HL_W * 2 * CS) >> 4);
+#pragma unroll
+            for (int g = 0; g < GROUPS0; ++g) {
+              if (g < ngroups) tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
+            }
+            acc = 1u;
+          }
+        }
+        tc::umma_commit(&empty[st]);
+      }
+      tc::umma_commit(done);
+    }
+  } else {
+    // ===================== epilogue (once per CTA) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    float* prow = p.partial + ((size_t)blockIdx.x * 128 + m) * PART_COLS;
+    if (b_end > b_begin) {
+      tc::mbar_wait(done, 0);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < ngroups * NCOLS; j += 16) {
+        uint32_t r[16];
+        tc::tmem_ld_x16(taddr + (uint32_t)j, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(prow + j + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                 __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+      }
+    } else {
+      for (int j = 0; j < ngroups * NCOLS; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512u);
+}
+
+// dw[co][ci][kd][kh][kw] (+)= sum over splits of the partial accumulators, fixed order
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
+                                       int u_is_x, int s_chunks, int ksplit, int accumulate) {
+  const int64_t total = (int64_t)Cout * Cin * 27;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 27);
+    const int ci = (int)((i / 27) % Cin);
+    const int co = (int)(i / (27 * (int64_t)Cin));
+    int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    int cu, cs;
+    if (u_is_x) { cu = ci; cs = co; kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
+    else { cu = co; cs = ci; }
+    const int g = kd * 3 + kh;
+    const int role = g >= GROUPS0 ? 1 : 0;
+    const int gl = g - role * GROUPS0;
+    const int wt = ((cu >> 7) * s_chunks + cs / CS) * 2 + role;
+    const float* src = partial + (((size_t)wt * ksplit) * 128 + (cu & 127)) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
+    float acc = 0.f;
+    for (int k = 0; k < ksplit; ++k) acc += src[(size_t)k * 128 * PART_COLS];
+    dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+
+struct WgPlan {
+  WgArgs a;
+  int u_is_x;
+  size_t partial_bytes, smem;
+  int grid;
+};
+
+bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
+  if (q->dtype != MEDNET_BF16 || q->gather != MEDNET_GATHER_CONV3) return false;
+  if (!mednet_device_has_tcgen05()) return false;
+  if (((uintptr_t)q->a | (uintptr_t)q->b) & 15) return false;
+  WgPlan pl;
+  // U = the operand with more channels (ties: dY); S = the other one, in chunks of 32 channels
+  pl.u_is_x = q->Cb > q->Ca ? 1 : 0;
+  const int CU = pl.u_is_x ? q->Cb : q->Ca, CSn = pl.u_is_x ? q->Ca : q->Cb;
+  if (CU % 64 != 0 || CSn % CS != 0) return false;
+  WgArgs& a = pl.a;
+  a.N = q->N; a.D = q->Da; a.H = q->Ha; a.W = q->Wa; a.CU = CU; a.CSn = CSn;
+  a.TD = q->Da >= 2 ? 2 : 1;
+  a.tiles_d = ceil_div(a.D, a.TD); a.tiles_h = ceil_div(a.H, BR_H); a.tiles_w = ceil_div(a.W, BR_W);
+  a.bricks = (int64_t)a.N * a.tiles_d * a.tiles_h * a.tiles_w;
+  a.u_tiles = ceil_div(CU, 128); a.s_chunks = CSn / CS;
+  const int worktypes = a.u_tiles * a.s_chunks * 2;
+  const int sms = sm_count_cached();
+  int64_t ksplit = (2 * sms + worktypes - 1) / worktypes;       // ~2 CTAs per SM in total: bounded tail
+  if (ksplit > a.bricks) ksplit = a.bricks;
+  if (ksplit < 1) ksplit = 1;
+  a.bricks_per_split = ceil_div64(a.bricks, ksplit);
+  a.ksplit = (int)ceil_div64(a.bricks, a.bricks_per_split);
+  pl.grid = worktypes * a.ksplit;
+  pl.partial_bytes = align_up((size_t)pl.grid * 128 * PART_COLS * sizeof(float), 256);
+  const size_t u_bytes = (size_t)2 * a.TD * 128 * 128;
+  const size_t s_bytes = align_up((size_t)(a.TD + 2) * HL_H * HL_W * 2 * CS, 1024);
+  pl.smem = 1024 + STAGES * (u_bytes + s_bytes) + 128;
+  if (pl.smem > 227 * 1024) return false;
+  *out = pl;
+  return true;
+}
+
+}  // namespace
+
+bool tc_wgrad_supported(const mednet_wgrad_params* q) {
+  WgPlan pl;
+  return plan_wgrad(q, &pl);
+}
+
+size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params* q) {
+  WgPlan pl;
+  if (!plan_wgrad(q, &pl)) return 0;
+  return pl.partial_bytes + colsum_workspace_bytes(q);
+}
+
+int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
+  WgPlan pl;
+  if (!plan_wgrad(q, &pl)) return MEDNET_EUNSUPPORTED;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return MEDNET_ENODRIVER;
+  WgArgs& a = pl.a;
+  a.partial = (float*)workspace;
+  const void* u_ptr = pl.u_is_x ? q->b : q->a;
+  const void* s_ptr = pl.u_is_x ? q->a : q->b;
+  CUtensorMap map_u, map_s;
+  {
+    const cuuint64_t C = (cuuint64_t)a.CU;
+    cuuint64_t dims[5] = {C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.N};
+    cuuint64_t strides[4] = {C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2, (cuuint64_t)a.D * a.H * a.W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)BR_W, (cuuint32_t)BR_H, (cuuint32_t)a.TD, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&map_u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(u_ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MEDNET_EUNSUPPORTED;
+  }
+  {
+    const cuuint64_t C = (cuuint64_t)a.CSn;
+    cuuint64_t dims[5] = {C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.N};
+    cuuint64_t strides[4] = {C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2, (cuuint64_t)a.D * a.H * a.W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)CS, (cuuint32_t)HL_W, (cuuint32_t)HL_H, (cuuint32_t)(a.TD + 2), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&map_s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s_ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MEDNET_EUNSUPPORTED;
+  }
+  static std::mutex mu;
+  static size_t configured = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (pl.smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = pl.smem;
+    }
+  }
+  wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
+  MEDNET_LAUNCH_CHECK();
+  const int64_t total = (int64_t)q->Ca * q->Cb * 27;
+  wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
+                                                               a.ksplit, q->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  if (q->dbias != nullptr) {
+    void* cpart = (char*)workspace + pl.partial_bytes;
+    return colsum_bias(q->a, q->dtype, (int64_t)q->N * q->Da * q->Ha * q->Wa, q->Ca, q->dbias, q->accumulate, cpart, st);
+  }
+  return MEDNET_OK;
+}
+
+}  // namespace mednet

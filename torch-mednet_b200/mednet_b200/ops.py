@@ -17,6 +17,7 @@ _DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2, torch.int64: 3}
 IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
 
 launch_count = 0          # kernels-API calls issued (bench.py reads it for `gpu_launches`)
+wgrad_events = []         # same, per wgrad launch (tensor-core or SIMT, whichever ran)
 conv_events = None        # when a list: (algorithmic FLOPs, start event, end event) per tcgen05 conv launch
 
 
@@ -187,18 +188,31 @@ def k_conv3(x, w_packed, nout, out_sp, gather, impl_id, bias=None, addend=None, 
     return y
 
 
+def wgrad_params(a, b, gather, impl="auto", dw=None, dbias=None):
+    n, da, ha, wa, ca = a.shape
+    _, db, hb, wb, cb = b.shape
+    return make("mednet_wgrad_params", a=_ptr(a), b=_ptr(b), dw=_ptr(dw), dbias=_ptr(dbias), N=n, Da=da, Ha=ha, Wa=wa,
+                Db=db, Hb=hb, Wb=wb, Ca=ca, Cb=cb, dtype=_dt(a), gather=gather, impl=IMPL[impl], accumulate=0)
+
+
 def k_wgrad(a, b, gather, impl="auto", want_bias=False):
     """dw (Ca,Cb,3,3,3) fp32 = sum_rows a[row] (x) b[gather(row, tap)]; optional bias gradient."""
     _need_cuda(a, b)
-    n, da, ha, wa, ca = a.shape
-    _, db, hb, wb, cb = b.shape
+    ca, cb = a.shape[-1], b.shape[-1]
     dw = torch.empty((ca, cb, 3, 3, 3), dtype=torch.float32, device=a.device)
     nb = ca if gather == 0 else cb
     dbias = torch.empty(nb, dtype=torch.float32, device=a.device) if want_bias else None
-    p = make("mednet_wgrad_params", a=_ptr(a), b=_ptr(b), dw=_ptr(dw), dbias=_ptr(dbias), N=n, Da=da, Ha=ha, Wa=wa, Db=db,
-             Hb=hb, Wb=wb, Ca=ca, Cb=cb, dtype=_dt(a), gather=gather, impl=IMPL[impl], accumulate=0)
+    p = wgrad_params(a, b, gather, impl, dw, dbias)
     ws = _ws(lib().mednet_conv3d_wgrad_workspace_bytes(_abi.C.byref(p)), a.device)
+    timing = conv_events is not None
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_wgrad")
+    if timing:
+        e1.record()
+        n, d, h, w = a.shape[:4]
+        wgrad_events.append((2.0 * n * d * h * w * ca * cb * 27, e0, e1))
     _count(2)
     return dw, dbias
 
