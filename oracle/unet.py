@@ -47,17 +47,44 @@ def groups_for(channels, num_groups):
     return g
 
 
-def single_conv(x, sd, prefix, order, num_groups):
+class Storage:
+    """Where a 16-bit pipeline rounds.  The reference keeps every tensor in fp32 (``Storage()`` = identity).
+    ``Storage.bf16()`` restates the SAME network with bfloat16 *storage*: every activation tensor that is
+    materialised between two ops (network input, GroupNorm(+activation) output, convolution(+activation)
+    output, residual join output) and every 3x3x3 convolution weight is rounded to bf16, all arithmetic stays
+    fp32 -- exactly what `model.to(torch.bfloat16)` / autocast does to the reference on a GPU, and what the
+    product's bf16 mode implements.  Used by the bf16 parity gate: this random-initialised network amplifies a
+    single bf16 rounding of its INPUT into ~1-2 % of logit error (tests/test_oracle_golden.py pins that), so
+    "bf16 result vs fp32 reference" measures the chaos of the network, not the correctness of the kernels;
+    "bf16 result vs the reference evaluated with bf16 storage" measures the kernels."""
+
+    def __init__(self, act=None, weight=None):
+        self.act = act if act is not None else (lambda t: t)
+        self.weight = weight if weight is not None else (lambda t: t)
+
+    @staticmethod
+    def bf16():
+        r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        return Storage(r, r)
+
+
+_FP32 = Storage()
+
+
+def single_conv(x, sd, prefix, order, num_groups, st=_FP32, join=None):
     """One order-string layer (components.py:12-67, :70-90).
 
     Note the reference re-binds ``num_groups`` inside its loop (components.py:53-54, quirk
     Q13); with a single 'g' per order string this has no further effect.
+    ``join``: optional (residual, non-linearity letter) applied after the last op of the layer
+    (components.py:177-178) before the result is stored.
     """
     assert "c" in order and order[0] not in _NONLIN
-    for ch in order:
+    n = len(order)
+    for i, ch in enumerate(order):
         if ch == "c":
             bias = sd.get(prefix + "conv.bias")       # present only without g/b (components.py:43)
-            x = F.conv3d(x, sd[prefix + "conv.weight"], bias, padding=1)
+            x = F.conv3d(x, st.weight(sd[prefix + "conv.weight"]), bias, padding=1)
         elif ch == "g":
             c = x.shape[1]
             x = F.group_norm(x, groups_for(c, num_groups), sd[prefix + "groupnorm.weight"],
@@ -66,45 +93,48 @@ def single_conv(x, sd, prefix, order, num_groups):
             x = _nonlinearity(x, ch)
         else:
             raise ValueError(f"Unsupported layer type '{ch}'")
+        last = i == n - 1
+        if last and join is not None:
+            x = _nonlinearity(x + join[0], join[1])
+        # a tensor is materialised after an op unless a non-linearity (fused into that op) follows
+        if last or order[i + 1] not in _NONLIN:
+            x = st.act(x)
     return x
 
 
-def double_conv(x, sd, prefix, order, num_groups):
+def double_conv(x, sd, prefix, order, num_groups, st=_FP32):
     """components.py:114-133 -- channel counts are implied by the weights."""
-    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups)
-    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups)
+    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups, st)
+    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups, st)
 
 
-def ext_resnet_block(x, sd, prefix, order, num_groups):
+def ext_resnet_block(x, sd, prefix, order, num_groups, st=_FP32):
     """components.py:168-180."""
-    out = single_conv(x, sd, prefix + "conv1.", order, num_groups)
+    out = single_conv(x, sd, prefix + "conv1.", order, num_groups, st)
     residual = out
-    out = single_conv(out, sd, prefix + "conv2.", order, num_groups)
+    out = single_conv(out, sd, prefix + "conv2.", order, num_groups, st)
     n_order = "".join(c for c in order if c not in _NONLIN)      # components.py:154-156
-    out = single_conv(out, sd, prefix + "conv3.", n_order, num_groups)
-    out = out + residual
-    if "l" in order:                                             # components.py:161-166
-        return F.leaky_relu(out, 0.1)
-    if "e" in order:
-        return F.elu(out)
-    return F.relu(out)
+    act = "l" if "l" in order else ("e" if "e" in order else "r")   # components.py:161-166
+    return single_conv(out, sd, prefix + "conv3.", n_order, num_groups, st, join=(residual, act))
 
 
 def unet3d_forward(sd, x, f_maps=64, layer_order="gcr", num_groups=8, testing=False,
-                   final_sigmoid=False):
+                   final_sigmoid=False, storage=_FP32):
     """UNet3D.forward, model.py:84-110."""
     f_maps = feature_ladder(f_maps, 4)
+    st = storage
+    x = st.act(x)
     skips = []
     for i in range(len(f_maps)):
         if i > 0:
             x = F.max_pool3d(x, 2)                               # components.py:210,224
-        x = double_conv(x, sd, f"encoders.{i}.basic_module.", layer_order, num_groups)
+        x = double_conv(x, sd, f"encoders.{i}.basic_module.", layer_order, num_groups, st)
         skips.insert(0, x)
     skips = skips[1:]
     for j, skip in enumerate(skips):
         x = F.interpolate(x, size=skip.shape[2:], mode="nearest")   # components.py:277-278
         x = torch.cat((skip, x), dim=1)                              # components.py:280
-        x = double_conv(x, sd, f"decoders.{j}.basic_module.", layer_order, num_groups)
+        x = double_conv(x, sd, f"decoders.{j}.basic_module.", layer_order, num_groups, st)
     x = F.conv3d(x, sd["final_conv.weight"], sd["final_conv.bias"])   # model.py:102
     if testing:
         x = torch.sigmoid(x) if final_sigmoid else torch.softmax(x, dim=1)
@@ -112,21 +142,23 @@ def unet3d_forward(sd, x, f_maps=64, layer_order="gcr", num_groups=8, testing=Fa
 
 
 def residual_unet3d_forward(sd, x, f_maps=32, conv_layer_order="cge", num_groups=8, testing=False,
-                            final_sigmoid=False, skip_final_activation=False):
+                            final_sigmoid=False, skip_final_activation=False, storage=_FP32):
     """ResidualUNet3D.forward, model.py:189-214."""
     f_maps = feature_ladder(f_maps, 5)
+    st = storage
+    x = st.act(x)
     skips = []
     for i in range(len(f_maps)):
         if i > 0:
             x = F.max_pool3d(x, 2)
-        x = ext_resnet_block(x, sd, f"encoders.{i}.basic_module.", conv_layer_order, num_groups)
+        x = ext_resnet_block(x, sd, f"encoders.{i}.basic_module.", conv_layer_order, num_groups, st)
         skips.insert(0, x)
     skips = skips[1:]
     for j, skip in enumerate(skips):
-        x = F.conv_transpose3d(x, sd[f"decoders.{j}.upsample.weight"], sd[f"decoders.{j}.upsample.bias"],
+        x = F.conv_transpose3d(x, st.weight(sd[f"decoders.{j}.upsample.weight"]), sd[f"decoders.{j}.upsample.bias"],
                                stride=2, padding=1, output_padding=1)   # components.py:259-264
-        x = x + skip                                                   # components.py:284
-        x = ext_resnet_block(x, sd, f"decoders.{j}.basic_module.", conv_layer_order, num_groups)
+        x = st.act(x + skip)                                           # components.py:284
+        x = ext_resnet_block(x, sd, f"decoders.{j}.basic_module.", conv_layer_order, num_groups, st)
     x = F.conv3d(x, sd["final_conv.weight"], sd["final_conv.bias"])    # model.py:207
     if testing and not skip_final_activation:
         x = torch.sigmoid(x) if final_sigmoid else torch.softmax(x, dim=1)

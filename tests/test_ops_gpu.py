@@ -65,6 +65,29 @@ def test_conv3_simt_fp32_fwd_bwd(cin, cout, shape, act):
     assert relerr(ncdhw(ag.grad), add.grad) < 1e-5
 
 
+@pytest.mark.parametrize("cin,cout,shape", [(1, 32, (5, 9, 70)), (1, 8, (3, 4, 5)), (2, 16, (4, 6, 7)), (4, 64, (2, 5, 66)),
+                                            (1, 24, (4, 4, 9))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_first_layer_small_channel_kernels(cin, cout, shape, dtype):
+    """in_channels = 1 layers (segmentation.py:30-31): few-input-channel fprop, few-output-channel dgrad and the
+    small-channel wgrad specialisations of the CUDA-core path (w-segments longer than 64 voxels included)."""
+    torch.manual_seed(cin * 10 + cout)
+    q = (lambda t: t.to(dtype).float())
+    x = q(torch.randn(2, cin, *shape)).requires_grad_()
+    w = q(torch.randn(cout, cin, 3, 3, 3) * 0.2).requires_grad_()
+    ref = F.elu(F.conv3d(x, w, None, padding=1))
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    xg = ndhwc(x.detach(), dtype).requires_grad_()
+    wg = w.detach().to(DEV).requires_grad_()
+    y = ops.Conv3x3Fn.apply(xg, wg, None, None, 3, "auto")
+    y.backward(ndhwc(g, dtype))
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert relerr(ncdhw(y.detach()), ref.detach()) < tol
+    assert relerr(ncdhw(xg.grad), x.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+    assert relerr(wg.grad.cpu(), w.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
 def test_conv3_simt_bf16_matches_bf16_rounded_reference():
     torch.manual_seed(3)
     x = torch.randn(1, 16, 6, 7, 8).bfloat16().float()

@@ -42,6 +42,8 @@ template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __f
 // V-wide vector load/store (V * sizeof(T) in {2,4,8,16} bytes, naturally aligned)
 // ------------------------------------------------------------------------------------------------
 template <int BYTES> struct RawVec;
+struct alignas(32) U32B { uint4 lo, hi; };
+template <> struct RawVec<32> { typedef U32B type; };
 template <> struct RawVec<16> { typedef uint4 type; };
 template <> struct RawVec<8> { typedef uint2 type; };
 template <> struct RawVec<4> { typedef uint32_t type; };

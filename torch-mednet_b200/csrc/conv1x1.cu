@@ -108,9 +108,96 @@ __global__ void conv1_dw_partial_kernel(const T* __restrict__ x, const float* __
   }
 }
 
-// db partial: block b sums dy[:, co, rows of block]
-__global__ void conv1_db_partial_kernel(const float* __restrict__ dy, float* __restrict__ partial_b, int64_t N,
-                                        int64_t S, int Cout, int64_t rows_per_block) {
+// Vectorised weight gradient for power-of-two Cin / V <= 32: thread (tx, ty) owns V input channels and walks rows
+// ty, ty+R, ... of one sample's slab (no 64-bit division in the loop: blockIdx.y = sample); CO_T output channels per
+// pass.  Row-lanes are combined with warp shuffles, warps through shared memory.
+// partial[(n*nblk + b)][co][ci]
+template <typename T, int V, int CO_T>
+__global__ void __launch_bounds__(256) conv1_dw_vec_kernel(const T* __restrict__ x, const float* __restrict__ dy,
+                                                           float* __restrict__ partial, int64_t S, int Cin, int Cout, int co0,
+                                                           int64_t rows_per_block) {
+  extern __shared__ float sm[];                                  // [8 warps][ncol][CO_T * V]
+  const int ncol = Cin / V, R = 256 / ncol;
+  const int tx = threadIdx.x % ncol, ty = threadIdx.x / ncol;
+  const int n = blockIdx.y;
+  const int64_t s0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t s1 = s0 + rows_per_block;
+  if (s1 > S) s1 = S;
+  const int nco = min(CO_T, Cout - co0);
+  float acc[CO_T][V];
+#pragma unroll
+  for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+  const T* xb = x + (int64_t)n * S * Cin + tx * V;
+  const float* dyb = dy + ((int64_t)n * Cout + co0) * S;
+  for (int64_t s = s0 + ty; s < s1; s += R) {
+    float xv[V];
+    load_vec<T, V>(xb + s * Cin, xv);
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+      if (j < nco) {
+        const float g = dyb[(int64_t)j * S + s];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[j][i] = fmaf(g, xv[i], acc[j][i]);
+      }
+    }
+  }
+  // rows that share a warp (lane = (ty % rpw) * ncol + tx when ncol < 32)
+  if (ncol < 32) {
+    for (int off = ncol; off < 32; off <<= 1)
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[j][i] += __shfl_xor_sync(0xffffffffu, acc[j][i], off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cols_in_warp = ncol < 32 ? ncol : 32;                // distinct tx values a warp holds
+  const int colw = ncol < 32 ? tx : lane;                        // this thread's column slot inside its warp
+  const int warps_per_colset = ncol < 32 ? 8 : 8 / (ncol / 32);  // warps holding the same columns
+  if (ncol >= 32 || lane < ncol) {
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) sm[((size_t)warp * cols_in_warp + colw) * (CO_T * V) + j * V + i] = acc[j][i];
+  }
+  __syncthreads();
+  // final: thread t < ncol * CO_T * V sums over the warps that hold its column
+  float* out = partial + ((int64_t)n * gridDim.x + blockIdx.x) * (int64_t)Cout * Cin;
+  for (int t = threadIdx.x; t < ncol * CO_T * V; t += 256) {
+    const int col = t / (CO_T * V), e = t % (CO_T * V), j = e / V, i = e % V;
+    if (j >= nco) continue;
+    float a = 0.f;
+    if (ncol < 32) {
+      for (int wp = 0; wp < 8; ++wp) a += sm[((size_t)wp * cols_in_warp + col) * (CO_T * V) + e];
+    } else {
+      const int wset = col / 32, cw = col % 32, nset = ncol / 32;
+      for (int k = 0; k < warps_per_colset; ++k) a += sm[((size_t)(k * nset + wset) * 32 + cw) * (CO_T * V) + e];
+    }
+    out[(int64_t)(co0 + j) * Cin + col * V + i] = a;
+  }
+}
+
+// db partial, per-sample blocks (blockIdx.y = sample): block sums dy[n, co, its rows]
+__global__ void conv1_db_partial_kernel(const float* __restrict__ dy, float* __restrict__ partial_b, int64_t S, int Cout,
+                                        int64_t rows_per_block) {
+  __shared__ float scratch[32];
+  const int n = blockIdx.y;
+  const int64_t s0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t s1 = s0 + rows_per_block;
+  if (s1 > S) s1 = S;
+  for (int co = 0; co < Cout; ++co) {
+    const float* src = dy + ((int64_t)n * Cout + co) * S;
+    float a = 0.f;
+    for (int64_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) a += src[s];
+    a = block_sum(a, scratch);
+    if (threadIdx.x == 0) partial_b[((int64_t)n * gridDim.x + blockIdx.x) * Cout + co] = a;
+  }
+}
+
+// db partial over flat row ranges (scalar path)
+__global__ void conv1_db_partial_rows_kernel(const float* __restrict__ dy, float* __restrict__ partial_b, int64_t N,
+                                             int64_t S, int Cout, int64_t rows_per_block) {
   __shared__ float scratch[32];
   const int64_t total = N * S;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -145,11 +232,14 @@ __global__ void conv1_dw_final_kernel(const float* __restrict__ partial, const f
 }
 
 struct Conv1Plan {
-  int nblocks, cin_t, cin_tiles, R;
+  int nblocks, cin_t, cin_tiles, R;     // scalar kernel: nblocks over all rows
   int64_t rows_per_block;
+  int vec, V, ncol, co_t, nblk_per_sample;   // vectorised kernel: nblk_per_sample blocks per sample
+  int64_t rows_per_block_vec;
 };
-static Conv1Plan conv1_plan(int64_t rows, int Cin) {
+static Conv1Plan conv1_plan(int64_t N, int64_t S, int Cin, int Cout, int elem_bytes) {
   Conv1Plan pl;
+  const int64_t rows = N * S;
   pl.cin_t = Cin < 256 ? Cin : 256;
   pl.cin_tiles = ceil_div(Cin, pl.cin_t);
   pl.R = 256 / pl.cin_t;
@@ -160,6 +250,19 @@ static Conv1Plan conv1_plan(int64_t rows, int Cin) {
   if (nb < 1) nb = 1;
   pl.rows_per_block = ceil_div64(rows, nb);
   pl.nblocks = (int)ceil_div64(rows, pl.rows_per_block);
+  // vectorised variant
+  pl.V = pick_vec(Cin, elem_bytes);
+  pl.ncol = Cin / pl.V;
+  pl.co_t = Cout <= 4 ? 4 : (Cout <= 8 ? 8 : 16);
+  pl.vec = (pl.ncol <= 16 && (pl.ncol & (pl.ncol - 1)) == 0 && pl.V * elem_bytes == 16 && N <= 65535 &&
+            (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float) <= 48 * 1024) ? 1 : 0;
+  int64_t per = ((int64_t)sm_count_cached() * 4 + N - 1) / N;
+  const int64_t maxper = S / ((256 / pl.ncol) * 8);
+  if (per > maxper) per = maxper;
+  if (per < 1) per = 1;
+  pl.rows_per_block_vec = ceil_div64(S, per);
+  pl.nblk_per_sample = (int)ceil_div64(S, pl.rows_per_block_vec);
+  if (pl.vec) pl.nblocks = (int)(N * pl.nblk_per_sample);
   return pl;
 }
 
@@ -184,7 +287,7 @@ extern "C" int mednet_conv1x1_fwd(const mednet_conv1_params* p, mednet_stream_t 
 
 extern "C" size_t mednet_conv1x1_bwd_workspace_bytes(const mednet_conv1_bwd_params* p) {
   if (!p || p->Cin <= 0 || p->Cout <= 0) return 0;
-  Conv1Plan pl = conv1_plan(p->N * p->S, p->Cin);
+  Conv1Plan pl = conv1_plan(p->N, p->S, p->Cin, p->Cout, dtype_bytes(p->dtype));
   return align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256) +
          align_up((size_t)pl.nblocks * p->Cout * sizeof(float), 256);
 }
@@ -205,22 +308,41 @@ extern "C" int mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* worksp
     });
     MEDNET_LAUNCH_CHECK();
   }
-  Conv1Plan pl = conv1_plan(p->N * p->S, p->Cin);
+  Conv1Plan pl = conv1_plan(p->N, p->S, p->Cin, p->Cout, dtype_bytes(p->dtype));
   float* partial = (float*)workspace;
   float* partial_b = (float*)((char*)workspace + align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256));
-  dim3 grid(pl.nblocks, pl.cin_tiles), block(pl.cin_t, pl.R);
-  const size_t sm2 = (size_t)pl.cin_t * pl.R * DW_MAX_CO * sizeof(float);
-  for (int co0 = 0; co0 < p->Cout; co0 += DW_MAX_CO) {
-    if (p->dtype == MEDNET_F32)
-      conv1_dw_partial_kernel<float><<<grid, block, sm2, stream>>>((const float*)p->x, p->dy, partial, p->N, p->S, p->Cin,
-                                                                  p->Cout, co0, pl.rows_per_block);
-    else
-      conv1_dw_partial_kernel<bf16><<<grid, block, sm2, stream>>>((const bf16*)p->x, p->dy, partial, p->N, p->S, p->Cin,
-                                                                 p->Cout, co0, pl.rows_per_block);
+  if (pl.vec) {
+    dim3 grid(pl.nblk_per_sample, (unsigned)p->N);
+    const size_t smv = (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float);
+    for (int co0 = 0; co0 < p->Cout; co0 += pl.co_t) {
+#define MEDNET_DWV(TT, VV, CT)                                                                                         \
+      conv1_dw_vec_kernel<TT, VV, CT><<<grid, 256, smv, stream>>>((const TT*)p->x, p->dy, partial, p->S, p->Cin, p->Cout, \
+                                                                  co0, pl.rows_per_block_vec)
+      if (p->dtype == MEDNET_F32) {
+        if (pl.co_t == 4) MEDNET_DWV(float, 4, 4); else if (pl.co_t == 8) MEDNET_DWV(float, 4, 8); else MEDNET_DWV(float, 4, 16);
+      } else {
+        if (pl.co_t == 4) MEDNET_DWV(bf16, 8, 4); else if (pl.co_t == 8) MEDNET_DWV(bf16, 8, 8); else MEDNET_DWV(bf16, 8, 16);
+      }
+#undef MEDNET_DWV
+      MEDNET_LAUNCH_CHECK();
+    }
+    conv1_db_partial_kernel<<<grid, 256, 0, stream>>>(p->dy, partial_b, p->S, p->Cout, pl.rows_per_block_vec);
+    MEDNET_LAUNCH_CHECK();
+  } else {
+    dim3 grid(pl.nblocks, pl.cin_tiles), block(pl.cin_t, pl.R);
+    const size_t sm2 = (size_t)pl.cin_t * pl.R * DW_MAX_CO * sizeof(float);
+    for (int co0 = 0; co0 < p->Cout; co0 += DW_MAX_CO) {
+      if (p->dtype == MEDNET_F32)
+        conv1_dw_partial_kernel<float><<<grid, block, sm2, stream>>>((const float*)p->x, p->dy, partial, p->N, p->S, p->Cin,
+                                                                    p->Cout, co0, pl.rows_per_block);
+      else
+        conv1_dw_partial_kernel<bf16><<<grid, block, sm2, stream>>>((const bf16*)p->x, p->dy, partial, p->N, p->S, p->Cin,
+                                                                   p->Cout, co0, pl.rows_per_block);
+      MEDNET_LAUNCH_CHECK();
+    }
+    conv1_db_partial_rows_kernel<<<pl.nblocks, 256, 0, stream>>>(p->dy, partial_b, p->N, p->S, p->Cout, pl.rows_per_block);
     MEDNET_LAUNCH_CHECK();
   }
-  conv1_db_partial_kernel<<<pl.nblocks, 256, 0, stream>>>(p->dy, partial_b, p->N, p->S, p->Cout, pl.rows_per_block);
-  MEDNET_LAUNCH_CHECK();
   const int tot = p->Cout * p->Cin + p->Cout;
   conv1_dw_final_kernel<<<ceil_div(tot, 128), 128, 0, stream>>>(partial, partial_b, p->dw, p->db, p->Cin, p->Cout,
                                                                pl.nblocks, p->accumulate);

@@ -301,6 +301,222 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict
 int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int accumulate, void* workspace,
                 cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------------
+// Small-channel specialisations of the stride-1 3x3x3 convolution.  The first layer of every reference
+// network has in_channels = 1 (midasmednet/segmentation.py:30-31, landmarks.py:30-31): its forward pass
+// is a 27-point stencil producing 8..64 channels, its dgrad a 27 x C -> 1 reduction and its wgrad
+// 27 x C accumulators over all voxels.  None of them is GEMM-shaped (K or N = 1), all three are bound by
+// the one wide activation they read or write; the generic 64x64 implicit-GEMM tile wastes 63/64 of its
+// work on them (measured 38 ms per launch at 8 x 128^3).
+// ------------------------------------------------------------------------------------------------
+
+// few INPUT channels (K <= 4): one thread per output voxel, NT output channels per thread
+template <typename T, int NT>
+__global__ void __launch_bounds__(128) conv3_fewin_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                          const float* __restrict__ bias, const T* __restrict__ addend,
+                                                          T* __restrict__ y, int D, int H, int W, int K, int Nout, int act,
+                                                          float act_param) {
+  extern __shared__ float sw[];                       // [27*K][NT] for output channels n0 .. n0+NT
+  const int n0 = blockIdx.z * NT, TK = 27 * K;
+  for (int i = threadIdx.x; i < TK * NT; i += blockDim.x) {
+    const int j = i % NT, tk = i / NT;
+    sw[i] = to_f32<T>(w[(int64_t)(n0 + j) * TK + tk]);
+  }
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W) return;
+  const int h = q / W, wq = q - h * W;
+  const int n = blockIdx.y / D, d = blockIdx.y - n * D;
+  float acc[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j] = bias != nullptr ? bias[n0 + j] : 0.f;
+  for (int kd = 0; kd < 3; ++kd) {
+    const int id = d + kd - 1;
+    if (id < 0 || id >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = h + kh - 1;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = wq + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        const T* xp = x + ((((int64_t)n * D + id) * H + ih) * W + iw) * K;
+        const float* wr = sw + (size_t)((kd * 3 + kh) * 3 + kw) * K * NT;
+        for (int k = 0; k < K; ++k) {
+          const float xv = to_f32<T>(xp[k]);
+#pragma unroll
+          for (int j = 0; j < NT; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + k * NT + j);
+            acc[j] = fmaf(xv, wv.x, acc[j]);
+            acc[j + 1] = fmaf(xv, wv.y, acc[j + 1]);
+            acc[j + 2] = fmaf(xv, wv.z, acc[j + 2]);
+            acc[j + 3] = fmaf(xv, wv.w, acc[j + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int64_t vox = (((int64_t)n * D + d) * H + h) * W + wq;
+#pragma unroll
+  for (int j = 0; j < NT; j += 8) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = acc[j + i];
+    if (addend != nullptr) {
+      float a8[8];
+      load_vec<T, 8>(addend + vox * Nout + n0 + j, a8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += a8[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_apply(o[i], act, act_param);
+    store_vec<T, 8>(y + vox * Nout + n0 + j, o);
+  }
+}
+
+// few OUTPUT channels (Nout <= 4, K = 8 * TPV): TPV threads per voxel, each owns 8 input channels (one 16-byte
+// load per tap: a warp reads whole cache lines), partial dot products combined with warp shuffles
+template <typename T, int TPV>
+__global__ void __launch_bounds__(128) conv3_fewout_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                           const float* __restrict__ bias, const T* __restrict__ addend,
+                                                           T* __restrict__ y, int D, int H, int W, int Nout, int act,
+                                                           float act_param) {
+  constexpr int K = 8 * TPV;
+  extern __shared__ float sw[];                       // [Nout][27][K]
+  for (int i = threadIdx.x; i < Nout * 27 * K; i += blockDim.x) sw[i] = to_f32<T>(w[i]);
+  __syncthreads();
+  const int sub = threadIdx.x % TPV;
+  const int q = blockIdx.x * (128 / TPV) + threadIdx.x / TPV;
+  const bool valid = q < H * W;
+  const int h = valid ? q / W : 0, wq = valid ? q - h * W : 0;
+  const int n = blockIdx.y / D, d = blockIdx.y - n * D;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    for (int kd = 0; kd < 3; ++kd) {
+      const int id = d + kd - 1;
+      if (id < 0 || id >= D) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = wq + kw - 1;
+          if (iw < 0 || iw >= W) continue;
+          float xv[8];
+          load_vec<T, 8>(x + ((((int64_t)n * D + id) * H + ih) * W + iw) * K + sub * 8, xv);
+          const int tap = (kd * 3 + kh) * 3 + kw;
+          for (int o = 0; o < Nout; ++o) {
+            const float* wr = sw + ((size_t)o * 27 + tap) * K + sub * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+            acc[o] = fmaf(xv[0], w0.x, fmaf(xv[1], w0.y, fmaf(xv[2], w0.z, fmaf(xv[3], w0.w, acc[o]))));
+            acc[o] = fmaf(xv[4], w1.x, fmaf(xv[5], w1.y, fmaf(xv[6], w1.z, fmaf(xv[7], w1.w, acc[o]))));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = TPV / 2; off > 0; off >>= 1)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+  if (valid && sub == 0) {
+    const int64_t vox = (((int64_t)n * D + d) * H + h) * W + wq;
+    for (int o = 0; o < Nout; ++o) {
+      float v = acc[o];
+      if (bias != nullptr) v += bias[o];
+      if (addend != nullptr) v += to_f32<T>(addend[vox * Nout + o]);
+      y[vox * Nout + o] = from_f32<T>(act_apply(v, act, act_param));
+    }
+  }
+}
+
+// weight gradient with few GATHERED channels (Cb <= 4): partial[block][ca][tap][cb]; a block walks 64-voxel
+// w-segments, thread (ca, tg) owns output channel ca and taps tg, tg+TG, ... (TG = 256 / Ca)
+constexpr int WSEG = 64, FEWIN_MAX_OWN = 7;
+template <typename T, int CB>
+__global__ void __launch_bounds__(256) wgrad_fewin_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                          float* __restrict__ partial, int N, int D, int H, int W, int Ca) {
+  extern __shared__ float sm[];
+  float* dys = sm;                                    // [WSEG][Ca]
+  float* xs = sm + WSEG * Ca;                         // [9][WSEG + 2][CB]
+  const int TG = 256 / Ca;
+  const int ca = threadIdx.x % Ca, tg = threadIdx.x / Ca;
+  const int wchunks = (W + WSEG - 1) / WSEG;
+  const int64_t segs = (int64_t)N * D * H * wchunks;
+  float acc[FEWIN_MAX_OWN][CB];
+  int xoff[FEWIN_MAX_OWN];
+#pragma unroll
+  for (int i = 0; i < FEWIN_MAX_OWN; ++i) {
+    const int t = tg + i * TG;
+    xoff[i] = t < 27 ? ((t / 3) * (WSEG + 2) + (t % 3)) * CB : -1;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) acc[i][c] = 0.f;
+  }
+  const int c8n = Ca / 8;
+  for (int64_t seg = blockIdx.x; seg < segs; seg += gridDim.x) {
+    int64_t t = seg;
+    const int w0 = (int)(t % wchunks) * WSEG; t /= wchunks;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    const int64_t rowbase = (((int64_t)n * D + d) * H + h) * W + w0;
+    for (int i = threadIdx.x; i < WSEG * c8n; i += 256) {
+      const int v = i / c8n, c8 = i - v * c8n;
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (w0 + v < W) load_vec<T, 8>(dy + (rowbase + v) * Ca + c8 * 8, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dys[v * Ca + c8 * 8 + k] = g[k];
+    }
+    for (int i = threadIdx.x; i < 9 * (WSEG + 2) * CB; i += 256) {
+      const int c = i % CB, wv = (i / CB) % (WSEG + 2), r = i / (CB * (WSEG + 2));
+      const int id = d + r / 3 - 1, ih = h + r % 3 - 1, iw = w0 + wv - 1;
+      float v = 0.f;
+      if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
+        v = to_f32<T>(x[((((int64_t)n * D + id) * H + ih) * W + iw) * CB + c]);
+      xs[i] = v;
+    }
+    __syncthreads();
+    for (int v = 0; v < WSEG; ++v) {
+      const float g = dys[v * Ca + ca];
+#pragma unroll
+      for (int i = 0; i < FEWIN_MAX_OWN; ++i) {
+        if (xoff[i] >= 0) {
+#pragma unroll
+          for (int c = 0; c < CB; ++c) acc[i][c] = fmaf(g, xs[xoff[i] + v * CB + c], acc[i][c]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < FEWIN_MAX_OWN; ++i) {
+    const int tp = tg + i * TG;
+    if (tp < 27) {
+#pragma unroll
+      for (int c = 0; c < CB; ++c) partial[(((int64_t)blockIdx.x * Ca + ca) * 27 + tp) * CB + c] = acc[i][c];
+    }
+  }
+}
+
+static bool fewin_fprop_ok(const mednet_conv3d_params* p) {
+  return p->gather == MEDNET_GATHER_CONV3 && p->K <= 4 && p->Nout % 8 == 0 && p->Nout <= 256 &&
+         (int64_t)p->N * p->Do <= 65535;
+}
+static bool fewout_fprop_ok(const mednet_conv3d_params* p) {
+  return p->gather == MEDNET_GATHER_CONV3 && p->Nout <= 4 && (p->K == 8 || p->K == 16 || p->K == 32 || p->K == 64) &&
+         (int64_t)p->N * p->Do <= 65535;
+}
+static bool fewin_wgrad_ok(const mednet_wgrad_params* p) {
+  return p->gather == MEDNET_GATHER_CONV3 && (p->Cb == 1 || p->Cb == 2 || p->Cb == 4) &&
+         (p->Ca == 8 || p->Ca == 16 || p->Ca == 32 || p->Ca == 64);
+}
+static int fewin_wgrad_blocks(const mednet_wgrad_params* p) {
+  const int64_t segs = (int64_t)p->N * p->Da * p->Ha * ceil_div(p->Wa, WSEG);
+  const int64_t cap = (int64_t)sm_count_cached() * 4;
+  return (int)(segs < cap ? segs : cap);
+}
+
+
 struct WgradPlan {
   int splits, colsum_blocks;
   int64_t rows_per_split, colsum_rows;
@@ -333,12 +549,37 @@ size_t colsum_workspace_bytes(const mednet_wgrad_params* p) {
 }
 
 size_t simt_wgrad_workspace_bytes(const mednet_wgrad_params* p) {
+  if (fewin_wgrad_ok(p))
+    return align_up((size_t)fewin_wgrad_blocks(p) * p->Ca * 27 * p->Cb * sizeof(float), 256) + colsum_workspace_bytes(p);
   WgradPlan pl = wgrad_plan(p);
   return align_up((size_t)pl.splits * p->Ca * 27 * p->Cb * sizeof(float), 256) + colsum_workspace_bytes(p);
 }
 
 template <typename T>
+static int fewin_wgrad_t(const mednet_wgrad_params* p, void* workspace, cudaStream_t st) {
+  const int blocks = fewin_wgrad_blocks(p);
+  float* partial = (float*)workspace;
+  const size_t pbytes = align_up((size_t)blocks * p->Ca * 27 * p->Cb * sizeof(float), 256);
+  const size_t smem = ((size_t)WSEG * p->Ca + 9 * (WSEG + 2) * p->Cb) * sizeof(float);
+  if (p->Cb == 1)
+    wgrad_fewin_kernel<T, 1><<<blocks, 256, smem, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+  else if (p->Cb == 2)
+    wgrad_fewin_kernel<T, 2><<<blocks, 256, smem, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+  else
+    wgrad_fewin_kernel<T, 4><<<blocks, 256, smem, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+  MEDNET_LAUNCH_CHECK();
+  const int64_t total = (int64_t)p->Ca * p->Cb * 27;
+  wgrad_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(partial, p->dw, p->Ca, p->Cb, blocks, p->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  if (p->dbias != nullptr)
+    return colsum_bias(p->a, p->dtype, (int64_t)p->N * p->Da * p->Ha * p->Wa, p->Ca, p->dbias, p->accumulate,
+                       (char*)workspace + pbytes, st);
+  return MEDNET_OK;
+}
+
+template <typename T>
 static int simt_wgrad_t(const mednet_wgrad_params* p, void* workspace, cudaStream_t st) {
+  if (fewin_wgrad_ok(p)) return fewin_wgrad_t<T>(p, workspace, st);
   WgradPlan pl = wgrad_plan(p);
   Geom g{p->N, p->Db, p->Hb, p->Wb, p->Da, p->Ha, p->Wa, p->gather};
   float* partial = (float*)workspace;
@@ -383,7 +624,34 @@ int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int ac
 }
 
 template <typename T>
+static int small_fprop_t(const mednet_conv3d_params* p, cudaStream_t st) {
+  const int HW = p->Ho * p->Wo;
+  if (fewin_fprop_ok(p)) {
+    const int NT = p->Nout % 32 == 0 ? 32 : (p->Nout % 16 == 0 ? 16 : 8);
+    dim3 grid(ceil_div(HW, 128), (unsigned)(p->N * p->Do), p->Nout / NT);
+    const size_t smem = (size_t)27 * p->K * NT * sizeof(float);
+#define MEDNET_FEWIN(NTV)                                                                                            \
+    conv3_fewin_kernel<T, NTV><<<grid, 128, smem, st>>>((const T*)p->x, (const T*)p->w, p->bias, (const T*)p->addend, \
+                                                        (T*)p->y, p->Do, p->Ho, p->Wo, p->K, p->Nout, p->act, p->act_param)
+    if (NT == 32) MEDNET_FEWIN(32); else if (NT == 16) MEDNET_FEWIN(16); else MEDNET_FEWIN(8);
+#undef MEDNET_FEWIN
+  } else {
+    const int TPV = p->K / 8;
+    dim3 grid(ceil_div(HW, 128 / TPV), (unsigned)(p->N * p->Do));
+    const size_t smem = (size_t)p->Nout * 27 * p->K * sizeof(float);
+#define MEDNET_FEWOUT(TP)                                                                                             \
+    conv3_fewout_kernel<T, TP><<<grid, 128, smem, st>>>((const T*)p->x, (const T*)p->w, p->bias, (const T*)p->addend, \
+                                                        (T*)p->y, p->Do, p->Ho, p->Wo, p->Nout, p->act, p->act_param)
+    if (TPV == 1) MEDNET_FEWOUT(1); else if (TPV == 2) MEDNET_FEWOUT(2); else if (TPV == 4) MEDNET_FEWOUT(4); else MEDNET_FEWOUT(8);
+#undef MEDNET_FEWOUT
+  }
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+template <typename T>
 static int simt_fprop_t(const mednet_conv3d_params* p, cudaStream_t st) {
+  if (fewin_fprop_ok(p) || fewout_fprop_ok(p)) return small_fprop_t<T>(p, st);
   Geom g{p->N, p->Di, p->Hi, p->Wi, p->Do, p->Ho, p->Wo, p->gather};
   const int64_t M = (int64_t)p->N * p->Do * p->Ho * p->Wo;
   MEDNET_REQUIRE(ceil_div(p->Nout, BN) <= 65535, MEDNET_EUNSUPPORTED);
