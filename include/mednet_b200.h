@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* mednet_stream_t;
 
-#define MEDNET_ABI_VERSION 1
+#define MEDNET_ABI_VERSION 2
 
 /* dtypes */
 #define MEDNET_F32  0
@@ -153,10 +153,21 @@ typedef struct {
   float*       dw;        /* [Cout, Cin]                              */
   float*       db;        /* [Cout]                                   */
   int64_t N, S; int32_t Cin, Cout, dtype; int32_t accumulate;
+  int32_t in_act; float in_act_param;   /* deferred activation derivative: dx *= in_act'(x), x = in_act(pre) (see below) */
 } mednet_conv1_bwd_params;
 size_t mednet_conv1x1_bwd_workspace_bytes(const mednet_conv1_bwd_params* p);
 int    mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* workspace, size_t workspace_bytes,
                           mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deferred activation derivative (`in_act`).  A convolution whose epilogue applies an activation
+ * (order 'gcr': conv -> ReLU) does not run a separate dpre = dy * act'(y) pass in backward.  Instead every
+ * CONSUMER of its output y (the next GroupNorm, MaxPool3d, the upsample/concat, the final 1x1x1 conv) is
+ * told `in_act` and multiplies the gradient it returns by act'(y), expressed through y itself -- its own
+ * input, which it reads anyway (ReLU: y > 0; LeakyReLU: y > 0 ? 1 : slope; ELU: y > 0 ? 1 : y + 1).  The
+ * mask is linear, so consumers that share y each apply it and autograd sums the results.
+ * ref: the in-place ReLU/LeakyReLU/ELU modules after the conv, mm/unet/components.py:35-40.
+ * ---------------------------------------------------------------------------------------------- */
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional residual add + activation), eps 1e-5, biased variance.
@@ -181,6 +192,7 @@ typedef struct {
   void*        dresidual; /* optional [N,S,C]: gradient wrt the residual input, or NULL       */
   float*       dgamma; float* dbeta;          /* [C]                                          */
   int64_t N, S; int32_t C, G, dtype, act; float act_param; int32_t accumulate;
+  int32_t in_act; float in_act_param;   /* deferred activation derivative of the PRODUCER of x: dx *= in_act'(x) */
 } mednet_gn_bwd_params;
 size_t mednet_groupnorm_bwd_workspace_bytes(const mednet_gn_bwd_params* p);
 int    mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
@@ -212,6 +224,8 @@ typedef struct {
 int mednet_maxpool3d_fwd(const mednet_pool_params* p, mednet_stream_t stream);
 typedef struct {
   const void* dy; const uint8_t* idx; void* dx; int32_t N, D, H, W, C, dtype;
+  const void* y;          /* pooled forward output (= x at the argmax); needed iff in_act != NONE       */
+  int32_t in_act; float in_act_param;   /* deferred activation derivative of the producer of x         */
 } mednet_pool_bwd_params;
 int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stream_t stream);
 /* Expand the 3-bit codes to ATen's int64 flat D*H*W indices, NCDHW order (parity checks only). */
@@ -231,8 +245,43 @@ typedef struct {
 int mednet_upsample_concat_fwd(const mednet_upcat_params* p, mednet_stream_t stream);
 typedef struct {
   const void* dout; void* dskip; void* dlow; int32_t N, D, H, W, d, h, w, Cs, Cl, dtype;
+  const void* skip; const void* low;    /* forward inputs; needed iff the matching *_act != NONE          */
+  int32_t skip_act, low_act; float skip_act_param, low_act_param;   /* deferred activation derivatives     */
 } mednet_upcat_bwd_params;
 int mednet_upsample_concat_bwd(const mednet_upcat_bwd_params* p, mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm over the VIRTUAL concat (skip, nearest-upsampled low): the decoder's first layer in order
+ * 'gcr' normalises cat((skip, up(low)), 1) (mm/unet/components.py:277-280 then :57).  The concat tensor is
+ * never materialised: statistics come from per-channel sums over skip and low (exact 2x upsampling
+ * replicates every low voxel 8 times), the apply pass reads skip/low and writes the normalised tensor the
+ * convolution consumes, and the backward pass writes dskip / dlow (sum over the 8 children) directly, with
+ * the deferred activation derivatives of the producers of skip / low applied.
+ * Requires D = 2d, H = 2h, W = 2w (otherwise MEDNET_EUNSUPPORTED: use upsample_concat + groupnorm).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void*  skip;      /* [N, D, H, W, Cs]                                                   */
+  const void*  low;       /* [N, d, h, w, Cl]                                                   */
+  const float* gamma; const float* beta;      /* [Cs + Cl]                                      */
+  void*        y;         /* [N, D, H, W, Cs + Cl] normalised concat                            */
+  float*       mean; float* rstd;             /* [N, G]                                         */
+  int32_t N, D, H, W, d, h, w, Cs, Cl, G, dtype; float eps;
+} mednet_upcat_gn_fwd_params;
+size_t mednet_upcat_groupnorm_fwd_workspace_bytes(const mednet_upcat_gn_fwd_params* p);
+int    mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
+                                  mednet_stream_t stream);
+typedef struct {
+  const void*  skip; const void* low; const void* dy;      /* dy [N, D, H, W, Cs + Cl]           */
+  const float* gamma; const float* mean; const float* rstd;
+  void*        dskip;     /* [N, D, H, W, Cs]                                                   */
+  void*        dlow;      /* [N, d, h, w, Cl]                                                   */
+  float*       dgamma; float* dbeta;          /* [Cs + Cl]                                      */
+  int32_t N, D, H, W, d, h, w, Cs, Cl, G, dtype, accumulate;
+  int32_t skip_act, low_act; float skip_act_param, low_act_param;
+} mednet_upcat_gn_bwd_params;
+size_t mednet_upcat_groupnorm_bwd_workspace_bytes(const mednet_upcat_gn_bwd_params* p);
+int    mednet_upcat_groupnorm_bwd(const mednet_upcat_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
+                                  mednet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Losses on NCDHW logits.  `logits` may be a channel slice of a wider tensor: element (n,c,s) lives

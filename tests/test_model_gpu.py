@@ -16,6 +16,7 @@ from mednet_b200.predict import SlidingWindowPredictor
 from mednet_b200.segmentation import SegmentationUNet3D
 from mednet_b200.unet.loss import DiceLoss, dice_metric
 from mednet_b200.unet.model import ResidualUNet3D, UNet3D
+from oracle import gates
 from oracle import steps as osteps
 from oracle import tiling as otiling
 from oracle import unet as ounet
@@ -96,12 +97,11 @@ def test_bf16_training_step_against_oracle(arch):
     (tests/test_oracle_golden.py::test_bf16_storage_sensitivity_of_the_reference), so the distance to the FP32
     reference is a property of the number format, not of the kernels; it is still bounded here by the distance the
     reference itself shows when evaluated in bf16.  The loss is gated at 1e-3 against the fp32 reference.
-    Gradients: the same chaos applies (the reference evaluated with bf16 forward storage and an fp32 backward
-    pass reaches only cos ~0.91-0.95 against its own fp32 gradients on the early encoder layers), so per
-    parameter tensor the bf16 product must be at least as close to the fp32 gradient as that bf16-storage
-    reference is (minus 0.03), and >= 0.999 wherever the reference itself is; the strict >= 0.999 cosine is
-    enforced per operator (tests/test_ops_gpu.py, test_tcgen05_gpu.py) and for the whole network in the fp32
-    validation mode (tests above)."""
+    Gradients: ReLU'/max-pool decisions flip under storage rounding, so the gradient error of ANY bf16 evaluation of
+    the 'gcr' net grows like sqrt(eps) (oracle/gates.py has the argument and the CPU test that pins it); the gate is
+    1 - cos(ours, fp32) <= max(1e-3, 2 * (1 - cos(bf16-storage reference, fp32))) per parameter tensor (tiny tensors
+    pooled), and the strict >= 0.999 for the smooth 'cge' ResidualUNet3D.  The strict cosine is also enforced per
+    operator (tests/test_ops_gpu.py, test_tcgen05_gpu.py) and for whole networks in the fp32 validation mode."""
     torch.manual_seed(0)
     f_maps = [16, 32, 64]
     if arch == "unet3d":
@@ -136,12 +136,13 @@ def test_bf16_training_step_against_oracle(arch):
     assert e_kernel < 1e-2
     assert e_total < 1.5 * e_format + 2e-3
     assert abs(loss.item() - ref_loss.item()) < 1e-3
-    worst = (2.0, None, None)
-    for k, p in net.named_parameters():
-        c_ours, c_fmt = cos(p.grad.cpu(), ref_grads[k]), cos(fmt_grads[k], ref_grads[k])
-        worst = min(worst, (c_ours, c_fmt, k))
-        assert c_ours > min(0.999, c_fmt - 0.03), (k, c_ours, c_fmt)
-    print(f"{arch}: worst gradient cosine vs fp32 reference {worst[0]:.4f} (bf16-storage reference: {worst[1]:.4f}) at {worst[2]}")
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    failures, rows = gates.format_aware_gradient_gate(ours, ref_grads, fmt_grads)
+    worst = min(rows, key=lambda r: r[1])
+    print(f"{arch}: worst gradient cosine vs fp32 reference {worst[1]:.4f} (bf16-storage reference: {worst[2]:.4f}) at {worst[0]}")
+    assert not failures, failures
+    if arch == "residual":                                        # smooth (ELU) network: the strict north-star gate holds in bf16
+        assert worst[1] > 0.999, worst
 
 
 def test_segmentation_training_loop_decreases_loss_and_checkpoint_roundtrip(tmp_path):

@@ -320,3 +320,99 @@ def test_heatmap_render_and_landmark_extraction():
     np.testing.assert_allclose(soft.cpu().numpy(), ohm.soft_argmax_landmarks(x, 0.7).numpy(), rtol=1e-4, atol=1e-4)
     u8 = torch.from_numpy(want)
     assert torch.equal(hm.extract_landmarks(u8.to(DEV)).cpu(), ohm.argmax_landmarks(u8))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Deferred activation derivative (include/mednet_b200.h): conv(+act) with defer_act=True followed by a consumer that
+# is told `in_act` must give the same gradients as the reference chain  act(conv(x)) -> consumer.
+# ---------------------------------------------------------------------------------------------------------------
+def _act_ref(pre, act):
+    return [pre, F.relu(pre), F.leaky_relu(pre, 0.1), F.elu(pre)][act]
+
+
+@pytest.mark.parametrize("act", [1, 2, 3])
+@pytest.mark.parametrize("consumer", ["groupnorm", "maxpool", "upcat_skip", "upcat_low", "conv1x1"])
+def test_deferred_activation_derivative(act, consumer):
+    torch.manual_seed(act)
+    cin, c = 6, 8
+    x = torch.randn(2, cin, 6, 8, 4, requires_grad=True)
+    w = (torch.randn(c, cin, 3, 3, 3) * 0.2).requires_grad_()
+    y = _act_ref(F.conv3d(x, w, None, padding=1), act)
+    xg = ndhwc(x.detach()).requires_grad_()
+    wg = w.detach().to(DEV).requires_grad_()
+    yg = ops.Conv3x3Fn.apply(xg, wg, None, None, act, "simt", True)
+    extra_ref, extra_got = [], []
+    if consumer == "groupnorm":
+        gamma, beta = (torch.rand(c) + 0.5).requires_grad_(), torch.randn(c).requires_grad_()
+        out = F.group_norm(y, 4, gamma, beta, 1e-5)
+        gg, bg = gamma.detach().to(DEV).requires_grad_(), beta.detach().to(DEV).requires_grad_()
+        got = ncdhw_keep(ops.GroupNormActFn.apply(yg, gg, bg, 4, 0, None, act))
+        extra_ref, extra_got = [gamma, beta], [gg, bg]
+    elif consumer == "maxpool":
+        out = F.max_pool3d(y, 2)
+        got = ncdhw_keep(ops.MaxPoolFn.apply(yg, act))
+    elif consumer == "upcat_skip":
+        low = torch.randn(2, 4, 3, 4, 2)
+        out = torch.cat((y, F.interpolate(low, size=y.shape[2:], mode="nearest")), dim=1)
+        got = ncdhw_keep(ops.UpsampleConcatFn.apply(yg, ndhwc(low), act, 0))
+    elif consumer == "upcat_low":
+        skip = torch.randn(2, 4, 12, 16, 8)
+        out = torch.cat((skip, F.interpolate(y, size=skip.shape[2:], mode="nearest")), dim=1)
+        got = ncdhw_keep(ops.UpsampleConcatFn.apply(ndhwc(skip), yg, 0, act))
+    else:
+        w1, b1 = (torch.randn(3, c, 1, 1, 1) * 0.3).requires_grad_(), torch.randn(3, requires_grad=True)
+        out = F.conv3d(y, w1, b1)
+        w1g, b1g = w1.detach().to(DEV).requires_grad_(), b1.detach().to(DEV).requires_grad_()
+        got = ops.Conv1x1Fn.apply(yg, w1g, b1g, act)
+        extra_ref, extra_got = [w1, b1], [w1g, b1g]
+    g = torch.randn_like(out)
+    out.backward(g)
+    got.backward(g.to(DEV))
+    assert relerr(got.detach().cpu(), out.detach()) < 1e-5
+    assert relerr(ncdhw(xg.grad), x.grad) < 1e-4
+    assert relerr(wg.grad.cpu(), w.grad) < 1e-4
+    for a, b in zip(extra_ref, extra_got):
+        assert relerr(b.grad.cpu(), a.grad) < 1e-4
+
+
+def ncdhw_keep(y):                           # (N,D,H,W,C) cuda -> (N,C,D,H,W) view that keeps the autograd graph
+    return y.permute(0, 4, 1, 2, 3)
+
+
+@pytest.mark.parametrize("cs,cl,groups,small", [(8, 16, 8, (3, 4, 2)), (64, 128, 8, (2, 2, 3)), (16, 8, 4, (4, 3, 5)),
+                                                (4, 4, 1, (2, 2, 2)), (6, 10, 8, (2, 3, 2))])
+@pytest.mark.parametrize("acts", [(0, 0), (1, 1), (3, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_groupnorm_over_virtual_concat(cs, cl, groups, small, acts, dtype):
+    """GroupNorm(cat(skip, up2(low))) without the concat tensor == F.interpolate + cat + group_norm of the reference
+    (components.py:277-280, :57), including groups that straddle the skip/low boundary (192 = 64 + 128 channels in
+    groups of 24) and the deferred activation derivatives of both producers."""
+    torch.manual_seed(cs + cl)
+    q = (lambda t: t.to(dtype).float())
+    big = tuple(2 * v for v in small)
+    C = cs + cl
+    sp = q(torch.randn(2, cs, *big) * 1.5).requires_grad_()      # pre-activations of the two producers
+    lp = q(torch.randn(2, cl, *small) + 0.3).requires_grad_()
+    skip, low = q(_act_ref(sp, acts[0])), q(_act_ref(lp, acts[1]))
+    # straight-through for the storage rounding of the activated tensors
+    skip = _act_ref(sp, acts[0]) + (skip - _act_ref(sp, acts[0])).detach()
+    low = _act_ref(lp, acts[1]) + (low - _act_ref(lp, acts[1])).detach()
+    gamma, beta = (torch.rand(C) + 0.5).requires_grad_(), torch.randn(C).requires_grad_()
+    ref = F.group_norm(torch.cat((skip, F.interpolate(low, size=big, mode="nearest")), dim=1), groups, gamma, beta, 1e-5)
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    sg, lg = ndhwc(skip.detach(), dtype).requires_grad_(), ndhwc(low.detach(), dtype).requires_grad_()
+    gg, bg = gamma.detach().to(DEV).requires_grad_(), beta.detach().to(DEV).requires_grad_()
+    assert ops.upcat_gn_supported(sg, lg)
+    y = ops.UpcatGroupNormFn.apply(sg, lg, gg, bg, groups, acts[0], acts[1])
+    y.backward(ndhwc(g, dtype))
+    f32 = dtype == torch.float32
+    assert relerr(ncdhw(y.detach()), ref.detach()) < (1e-5 if f32 else 1.5e-2)
+    assert relerr(ncdhw(sg.grad), sp.grad) < (2e-4 if f32 else 3e-2)
+    assert relerr(ncdhw(lg.grad), lp.grad) < (2e-4 if f32 else 3e-2)
+    assert relerr(gg.grad.cpu(), gamma.grad) < (1e-4 if f32 else 3e-2)
+    assert relerr(bg.grad.cpu(), beta.grad) < (1e-4 if f32 else 3e-2)
+    # identical to the unfused composition of the same kernels (upsample_concat -> groupnorm)
+    y2 = ops.GroupNormActFn.apply(ops.UpsampleConcatFn.apply(sg.detach(), lg.detach()), gg.detach(), bg.detach(), groups, 0, None)
+    assert relerr(y.detach().float().cpu(), y2.float().cpu()) < (1e-6 if f32 else 8e-3)
+    assert not ops.upcat_gn_supported(sg, lg[:, :1])             # non-2x geometry -> unfused path

@@ -149,3 +149,49 @@ def test_bf16_storage_sensitivity_of_the_reference():
     assert 1e-2 < rel(full) < 1e-1
     # identity storage is the fp32 reference itself
     assert torch.equal(ounet.unet3d_forward(sd, x, f_maps=f_maps, storage=ounet.Storage()), ref)
+
+
+def test_gradient_sensitivity_is_decision_flip_noise():
+    """Pins the argument of oracle/gates.py on the CPU.  With activations AND weights stored at k significant bits
+    (fp32 arithmetic, straight-through rounding) the angular error 1 - cos of the ReLU U-Net's early-layer gradients
+    against fp32 scales ~linearly with eps = 2^-k, i.e. the gradient error goes like sqrt(eps): the signature of
+    ReLU'/max-pool decisions flipping (a fraction ~eps of them, O(1) change each), not of smooth error propagation
+    (which would give 1 - cos ~ eps^2).  At k = 8 (bf16) that puts the reference itself at cos < 0.99; the smooth
+    ELU ResidualUNet3D under the same storage stays >= 0.999."""
+    import torch
+    from oracle import gates, loss as oloss, steps as osteps, unet as ounet
+
+    def rbits(k):
+        def r(t):
+            m, e = torch.frexp(t.detach())
+            return t + (torch.ldexp(torch.round(m * 2 ** k) / 2 ** k, e) - t).detach()
+        return r
+
+    torch.manual_seed(0)
+    f_maps = [16, 32, 64]
+    x = torch.randn(2, 1, 16, 32, 16)
+    y = torch.randint(0, 3, (2, 16, 32, 16))
+    w = torch.tensor([0.2, 1.0, 0.7])
+    key = "encoders.0.basic_module.SingleConv2.conv.weight"
+    sd = osteps.leaf_state_dict(ounet.make_unet3d_state_dict(1, 3, f_maps))
+    ref = osteps.grads_of(oloss.dice_loss(ounet.unet3d_forward(sd, x, f_maps=f_maps), y, weight=w), sd)
+    ang = {}
+    for k in (8, 11, 14):
+        leaf = osteps.leaf_state_dict(sd)
+        st = ounet.Storage(rbits(k), rbits(k))
+        g = osteps.grads_of(oloss.dice_loss(ounet.unet3d_forward(leaf, x, f_maps=f_maps, storage=st), y, weight=w), leaf)
+        ang[k] = 1.0 - gates.cosine(g[key], ref[key])
+    assert ang[8] > 1e-2                                  # the reference in bf16 misses cos >= 0.999 by > 10x
+    assert 3.0 < ang[8] / ang[11] < 30.0                  # ~8x per 3 bits (linear in eps), not 64x (quadratic)
+    assert 3.0 < ang[11] / ang[14] < 30.0
+    # k-bit rounding with k = 8 IS bfloat16 rounding
+    t = torch.randn(1000)
+    assert torch.equal(rbits(8)(t), t.to(torch.bfloat16).float())
+    # smooth network: strict gate holds under bf16 storage
+    sdr = osteps.leaf_state_dict(ounet.make_residual_unet3d_state_dict(1, 3, f_maps))
+    fr = lambda s, **kw: ounet.residual_unet3d_forward(s, x, f_maps=f_maps, **kw)
+    ref_r = osteps.grads_of(oloss.dice_loss(fr(sdr), y, weight=w), sdr)
+    leaf = osteps.leaf_state_dict(sdr)
+    fmt_r = osteps.grads_of(oloss.dice_loss(fr(leaf, storage=ounet.Storage.bf16()), y, weight=w), leaf)
+    failures, rows = gates.format_aware_gradient_gate(fmt_r, ref_r, fmt_r)
+    assert not failures and min(r[1] for r in rows) > 0.999, rows

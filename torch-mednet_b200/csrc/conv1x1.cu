@@ -41,10 +41,65 @@ __global__ void conv1_fwd_kernel(const T* __restrict__ x, const float* __restric
   }
 }
 
-// dx[r][ci] = sum_co dy[n][co][s] * w[co][ci]
+
+// Coalesced forward for power-of-two Cin / V <= 32 (16-byte vectors): `ncol` adjacent lanes share one voxel row
+// (one fully used 16 B x ncol line per row), partial dot products are combined with warp shuffles, the block's
+// 256 voxels x CO_T results are staged in shared memory and written as contiguous NCDHW runs.
+template <typename T, int V, int CO_T>
+__global__ void __launch_bounds__(256) conv1_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            int64_t total, int64_t S, int Cin, int Cout) {
+  __shared__ float tile[CO_T][256];
+  const int ncol = Cin / V, vpp = 256 / ncol;                  // voxels per pass
+  const int col = threadIdx.x % ncol, vl = threadIdx.x / ncol;
+  for (int co0 = 0; co0 < Cout; co0 += CO_T) {
+    const int nco = min(CO_T, Cout - co0);
+    float wr[CO_T][V];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) wr[j][i] = j < nco ? w[(co0 + j) * Cin + col * V + i] : 0.f;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
+      for (int ps = 0; ps < ncol; ++ps) {
+        const int vb = ps * vpp + vl;                            // voxel slot inside the block's 256
+        const int64_t r = base + vb;
+        float acc[CO_T];
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+        if (r < total) {
+          float xv[V];
+          load_vec<T, V>(x + r * Cin + col * V, xv);
+#pragma unroll
+          for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[j] = fmaf(xv[i], wr[j][i], acc[j]);
+        }
+        for (int off = 1; off < ncol; off <<= 1)
+#pragma unroll
+          for (int j = 0; j < CO_T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+        if (col == 0) {
+#pragma unroll
+          for (int j = 0; j < CO_T; ++j) tile[j][vb] = acc[j];
+        }
+      }
+      __syncthreads();
+      const int64_t r = base + threadIdx.x;
+      if (r < total) {
+        const int64_t n = r / S, sidx = r - n * S;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j)
+          if (j < nco) y[(n * Cout + co0 + j) * S + sidx] = tile[j][threadIdx.x] + bias[co0 + j];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// dx[r][ci] = sum_co dy[n][co][s] * w[co][ci]  (times in_act'(x) when the producer's activation is deferred)
 template <typename T, int V>
 __global__ void conv1_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx,
-                                int64_t N, int64_t S, int Cin, int Cout) {
+                                int64_t N, int64_t S, int Cin, int Cout, const T* __restrict__ x, int in_act,
+                                float in_act_param) {
   extern __shared__ float sw[];  // [Cout][Cin]
   for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -61,6 +116,12 @@ __global__ void conv1_dx_kernel(const float* __restrict__ dy, const float* __res
         const float* wr = sw + co * Cin + k;
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = fmaf(g, wr[i], acc[i]);
+      }
+      if (in_act != MEDNET_ACT_NONE) {
+        float xv[V];
+        load_vec<T, V>(x + r * Cin + k, xv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] *= act_grad_from_out(xv[i], in_act, in_act_param);
       }
       store_vec<T, V>(out + k, acc);
     }
@@ -115,7 +176,8 @@ __global__ void conv1_dw_partial_kernel(const T* __restrict__ x, const float* __
 template <typename T, int V, int CO_T>
 __global__ void __launch_bounds__(256) conv1_dw_vec_kernel(const T* __restrict__ x, const float* __restrict__ dy,
                                                            float* __restrict__ partial, int64_t S, int Cin, int Cout, int co0,
-                                                           int64_t rows_per_block) {
+                                                           int64_t rows_per_block, const float* __restrict__ w,
+                                                           T* __restrict__ dx, int in_act, float in_act_param) {
   extern __shared__ float sm[];                                  // [8 warps][ncol][CO_T * V]
   const int ncol = Cin / V, R = 256 / ncol;
   const int tx = threadIdx.x % ncol, ty = threadIdx.x / ncol;
@@ -131,15 +193,48 @@ __global__ void __launch_bounds__(256) conv1_dw_vec_kernel(const T* __restrict__
     for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
   const T* xb = x + (int64_t)n * S * Cin + tx * V;
   const float* dyb = dy + ((int64_t)n * Cout + co0) * S;
-  for (int64_t s = s0 + ty; s < s1; s += R) {
-    float xv[V];
-    load_vec<T, V>(xb + s * Cin, xv);
+  if (dx != nullptr) {
+    // fused input gradient (single pass: Cout <= CO_T): x and dy are read ONCE for dx, dw and db;
+    // dx = (sum_co dy[co] * w[co][ci]) * in_act'(x)
+    float wr[CO_T][V];
 #pragma unroll
-    for (int j = 0; j < CO_T; ++j) {
-      if (j < nco) {
-        const float g = dyb[(int64_t)j * S + s];
+    for (int j = 0; j < CO_T; ++j)
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[j][i] = fmaf(g, xv[i], acc[j][i]);
+      for (int i = 0; i < V; ++i) wr[j][i] = j < nco ? w[(co0 + j) * Cin + tx * V + i] : 0.f;
+    T* dxb = dx + (int64_t)n * S * Cin + tx * V;
+    for (int64_t s = s0 + ty; s < s1; s += R) {
+      float xv[V], o[V];
+      load_vec<T, V>(xb + s * Cin, xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) {
+        if (j < nco) {
+          const float g = dyb[(int64_t)j * S + s];
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            acc[j][i] = fmaf(g, xv[i], acc[j][i]);
+            o[i] = fmaf(g, wr[j][i], o[i]);
+          }
+        }
+      }
+      if (in_act != MEDNET_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] *= act_grad_from_out(xv[i], in_act, in_act_param);
+      }
+      store_vec<T, V>(dxb + s * Cin, o);
+    }
+  } else {
+    for (int64_t s = s0 + ty; s < s1; s += R) {
+      float xv[V];
+      load_vec<T, V>(xb + s * Cin, xv);
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) {
+        if (j < nco) {
+          const float g = dyb[(int64_t)j * S + s];
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[j][i] = fmaf(g, xv[i], acc[j][i]);
+        }
       }
     }
   }
@@ -277,6 +372,18 @@ extern "C" int mednet_conv1x1_fwd(const mednet_conv1_params* p, mednet_stream_t 
   const size_t smem = (size_t)p->Cin * p->Cout * sizeof(float);
   MEDNET_REQUIRE(smem <= 48 * 1024, MEDNET_EUNSUPPORTED);
   const int V = pick_vec(p->Cin, dtype_bytes(p->dtype));
+  const int ncol = p->Cin / V;
+  if (V * dtype_bytes(p->dtype) == 16 && ncol <= 32 && (ncol & (ncol - 1)) == 0) {
+    const int64_t total = p->N * p->S;
+    const int grid = grid_for(ceil_div64(total, 256) * 256, 256, 8);
+#define MEDNET_C1F(TT, VV, CT) \
+    conv1_fwd_vec_kernel<TT, VV, CT><<<grid, 256, 0, stream>>>((const TT*)p->x, p->w, p->bias, p->y, total, p->S, p->Cin, p->Cout)
+    if (p->dtype == MEDNET_F32) { if (p->Cout <= 4) MEDNET_C1F(float, 4, 4); else MEDNET_C1F(float, 4, 8); }
+    else { if (p->Cout <= 4) MEDNET_C1F(bf16, 8, 4); else MEDNET_C1F(bf16, 8, 8); }
+#undef MEDNET_C1F
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  }
   MEDNET_DISPATCH_TV(p->dtype, V, {
     conv1_fwd_kernel<T, VV><<<grid_for(p->N * p->S, 128, 16), 128, smem, stream>>>((const T*)p->x, p->w, p->bias, p->y,
                                                                                   p->N, p->S, p->Cin, p->Cout);
@@ -301,14 +408,16 @@ extern "C" int mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* worksp
   const size_t smem = (size_t)p->Cin * p->Cout * sizeof(float);
   MEDNET_REQUIRE(smem <= 48 * 1024, MEDNET_EUNSUPPORTED);
   const int V = pick_vec(p->Cin, dtype_bytes(p->dtype));
-  if (p->dx != nullptr) {
+  Conv1Plan pl = conv1_plan(p->N, p->S, p->Cin, p->Cout, dtype_bytes(p->dtype));
+  const bool fuse_dx = p->dx != nullptr && pl.vec && p->Cout <= pl.co_t;     // one pass over x and dy for dx, dw, db
+  if (p->dx != nullptr && !fuse_dx) {
     MEDNET_DISPATCH_TV(p->dtype, V, {
       conv1_dx_kernel<T, VV><<<grid_for(p->N * p->S, 128, 16), 128, smem, stream>>>(p->dy, p->w, (T*)p->dx, p->N, p->S,
-                                                                                   p->Cin, p->Cout);
+                                                                                   p->Cin, p->Cout, (const T*)p->x, p->in_act,
+                                                                                   p->in_act_param);
     });
     MEDNET_LAUNCH_CHECK();
   }
-  Conv1Plan pl = conv1_plan(p->N, p->S, p->Cin, p->Cout, dtype_bytes(p->dtype));
   float* partial = (float*)workspace;
   float* partial_b = (float*)((char*)workspace + align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256));
   if (pl.vec) {
@@ -317,7 +426,8 @@ extern "C" int mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* worksp
     for (int co0 = 0; co0 < p->Cout; co0 += pl.co_t) {
 #define MEDNET_DWV(TT, VV, CT)                                                                                         \
       conv1_dw_vec_kernel<TT, VV, CT><<<grid, 256, smv, stream>>>((const TT*)p->x, p->dy, partial, p->S, p->Cin, p->Cout, \
-                                                                  co0, pl.rows_per_block_vec)
+                                                                  co0, pl.rows_per_block_vec, p->w,                    \
+                                                                  fuse_dx ? (TT*)p->dx : nullptr, p->in_act, p->in_act_param)
       if (p->dtype == MEDNET_F32) {
         if (pl.co_t == 4) MEDNET_DWV(float, 4, 4); else if (pl.co_t == 8) MEDNET_DWV(float, 4, 8); else MEDNET_DWV(float, 4, 16);
       } else {

@@ -92,7 +92,8 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
 
 template <typename T, int V>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
-                                   int N, int D, int H, int W, int C) {
+                                   int N, int D, int H, int W, int C, const T* __restrict__ y, int in_act,
+                                   float in_act_param) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2, ncol = C / V;
   const int64_t total = (int64_t)N * D * H * W * ncol;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -111,6 +112,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
       const int mine = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
       float gy[V];
       load_vec<T, V>(dy + o, gy);
+      if (in_act != MEDNET_ACT_NONE) {     // deferred derivative of the producer's activation: x[argmax] == y
+        float yv[V];
+        load_vec<T, V>(y + o, yv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) gy[j] *= act_grad_from_out(yv[j], in_act, in_act_param);
+      }
       union { typename RawVec<V>::type r; uint8_t b[V]; } u;
       u.r = *reinterpret_cast<const typename RawVec<V>::type*>(idx + o);
 #pragma unroll
@@ -182,7 +189,8 @@ __device__ __forceinline__ int nearest_first_dst(int s, float scale, int in_size
 }
 
 template <typename T, int V>
-__global__ void upcat_bwd_skip_kernel(const T* __restrict__ dout, T* __restrict__ dskip, int64_t vox, int Cs, int Cl) {
+__global__ void upcat_bwd_skip_kernel(const T* __restrict__ dout, T* __restrict__ dskip, int64_t vox, int Cs, int Cl,
+                                      const T* __restrict__ skip, int act, float act_param) {
   const int ncs = Cs / V;
   const int64_t total = vox * ncs;
   const int C = Cs + Cl;
@@ -190,13 +198,23 @@ __global__ void upcat_bwd_skip_kernel(const T* __restrict__ dout, T* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % ncs);
     const int64_t v = i / ncs;
-    *reinterpret_cast<R*>(dskip + i * V) = *reinterpret_cast<const R*>(dout + v * C + cv * V);
+    if (act == MEDNET_ACT_NONE) {
+      *reinterpret_cast<R*>(dskip + i * V) = *reinterpret_cast<const R*>(dout + v * C + cv * V);
+    } else {
+      float g[V], xv[V];
+      load_vec<T, V>(dout + v * C + cv * V, g);
+      load_vec<T, V>(skip + i * V, xv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] *= act_grad_from_out(xv[j], act, act_param);
+      store_vec<T, V>(dskip + i * V, g);
+    }
   }
 }
 
 template <typename T, int V>
 __global__ void upcat_bwd_low_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, int D, int H, int W,
-                                     int d, int h, int w, int Cs, int Cl) {
+                                     int d, int h, int w, int Cs, int Cl, const T* __restrict__ low, int act,
+                                     float act_param) {
   const int C = Cs + Cl, ncl = Cl / V;
   const float sd = (float)d / (float)D, sh = (float)h / (float)H, sw = (float)w / (float)W;
   const int64_t total = (int64_t)N * d * h * w * ncl;
@@ -221,6 +239,12 @@ __global__ void upcat_bwd_low_kernel(const T* __restrict__ dout, T* __restrict__
 #pragma unroll
           for (int j = 0; j < V; ++j) acc[j] += g[j];
         }
+    if (act != MEDNET_ACT_NONE) {
+      float xv[V];
+      load_vec<T, V>(low + i * V, xv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] *= act_grad_from_out(xv[j], act, act_param);
+    }
     store_vec<T, V>(dlow + i * V, acc);
   }
 }
@@ -254,13 +278,15 @@ extern "C" int mednet_maxpool3d_fwd(const mednet_pool_params* p, mednet_stream_t
 
 extern "C" int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->dy && p->idx && p->dx, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->in_act == MEDNET_ACT_NONE || p->y != nullptr, MEDNET_EINVAL);
   MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
   MEDNET_REQUIRE(p->N > 0 && p->C > 0 && p->D >= 2 && p->H >= 2 && p->W >= 2, MEDNET_EINVAL);
   const int V = pick_vec(p->C, dtype_bytes(p->dtype));
   const int64_t total = (int64_t)p->N * p->D * p->H * p->W * (p->C / V);
   MEDNET_DISPATCH_TV(p->dtype, V, {
     maxpool_bwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->dy, p->idx, (T*)p->dx, p->N, p->D,
-                                                                       p->H, p->W, p->C);
+                                                                       p->H, p->W, p->C, (const T*)p->y, p->in_act,
+                                                                       p->in_act_param);
   });
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
@@ -294,6 +320,8 @@ extern "C" int mednet_upsample_concat_fwd(const mednet_upcat_params* p, mednet_s
 
 extern "C" int mednet_upsample_concat_bwd(const mednet_upcat_bwd_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->dout && p->dlow && (p->dskip || p->Cs == 0), MEDNET_EINVAL);
+  MEDNET_REQUIRE((p->skip_act == MEDNET_ACT_NONE || p->Cs == 0 || p->skip) && (p->low_act == MEDNET_ACT_NONE || p->low),
+                 MEDNET_EINVAL);
   MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
   MEDNET_REQUIRE(p->N > 0 && p->D > 0 && p->H > 0 && p->W > 0 && p->d > 0 && p->h > 0 && p->w > 0 && p->Cs >= 0 &&
                      p->Cl > 0, MEDNET_EINVAL);
@@ -303,11 +331,12 @@ extern "C" int mednet_upsample_concat_bwd(const mednet_upcat_bwd_params* p, medn
   const int64_t tl = (int64_t)p->N * p->d * p->h * p->w * (p->Cl / V);
   MEDNET_DISPATCH_TV(p->dtype, V, {
     if (p->Cs > 0) {
-      upcat_bwd_skip_kernel<T, VV><<<grid_for(vox * (p->Cs / VV), 256), 256, 0, stream>>>((const T*)p->dout,
-                                                                                        (T*)p->dskip, vox, p->Cs, p->Cl);
+      upcat_bwd_skip_kernel<T, VV><<<grid_for(vox * (p->Cs / VV), 256), 256, 0, stream>>>(
+          (const T*)p->dout, (T*)p->dskip, vox, p->Cs, p->Cl, (const T*)p->skip, p->skip_act, p->skip_act_param);
     }
     upcat_bwd_low_kernel<T, VV><<<grid_for(tl, 256), 256, 0, stream>>>((const T*)p->dout, (T*)p->dlow, p->N, p->D, p->H,
-                                                                      p->W, p->d, p->h, p->w, p->Cs, p->Cl);
+                                                                      p->W, p->d, p->h, p->w, p->Cs, p->Cl,
+                                                                      (const T*)p->low, p->low_act, p->low_act_param);
   });
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;

@@ -16,9 +16,9 @@ struct SlabPlan {
   int64_t rows_per_slab;
 };
 
-static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes) {
+static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force_v = 0) {
   SlabPlan p;
-  p.V = pick_vec(C, elem_bytes);
+  p.V = force_v > 0 ? force_v : pick_vec(C, elem_bytes);
   p.ncol = C / p.V;
   if (p.ncol <= 256) {
     p.ncol_t = p.ncol;
@@ -264,7 +264,7 @@ template <typename T, int V>
 __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                     const float* __restrict__ coef, T* __restrict__ dx,
                                     T* __restrict__ dresidual, int64_t S, int C, int ncol,
-                                    int64_t rows_per_slab, int act, float act_param) {
+                                    int64_t rows_per_slab, int act, float act_param, int in_act, float in_act_param) {
   const int col = blockIdx.z * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const int n = blockIdx.y, slab = blockIdx.x;
@@ -290,8 +290,14 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
       for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
     }
     if (dresidual != nullptr) store_vec<T, V>(dresidual + base + r * C, gv);
+    if (in_act != MEDNET_ACT_NONE) {            // deferred derivative of the activation that produced x
 #pragma unroll
-    for (int i = 0; i < V; ++i) xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i]));
+      for (int i = 0; i < V; ++i)
+        xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], in_act, in_act_param);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i]));
+    }
     store_vec<T, V>(dx + base + r * C, xv);
   }
 }
@@ -317,6 +323,204 @@ __global__ void act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy
 #pragma unroll
     for (int k = 0; k < V; ++k) gv[k] *= act_grad_from_out(yv[k], act, a);
     store_vec<T, V>(dx + i * V, gv);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm over the VIRTUAL concat cat((skip, nearest_up2(low)), channel): the concat tensor is never
+// materialised (mednet_upcat_groupnorm_fwd / _bwd).  Exact 2x upsampling: every low voxel has 8 children.
+// ------------------------------------------------------------------------------------------------
+// one block per (n, g): statistics from the per-channel partial sums of skip (pa) and low (pb, weight 8)
+__global__ void upcat_gn_finalize_kernel(const float* __restrict__ pa, const float* __restrict__ pb,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ ab,
+                                         int64_t S, int Cs, int Cl, int G, int nslab_a, int nslab_b, float eps) {
+  __shared__ double scratch[32];
+  __shared__ float s_mean, s_rstd;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int C = Cs + Cl, cpg = C / G;
+  const int nslab = nslab_a > nslab_b ? nslab_a : nslab_b;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < nslab * cpg; i += blockDim.x) {
+    const int slab = i / cpg, c = g * cpg + i % cpg;
+    if (c < Cs) {
+      if (slab < nslab_a) {
+        const float* p = pa + ((int64_t)n * nslab_a + slab) * 2 * Cs;
+        s += (double)p[c];
+        q += (double)p[Cs + c];
+      }
+    } else if (slab < nslab_b) {
+      const float* p = pb + ((int64_t)n * nslab_b + slab) * 2 * Cl;
+      s += 8.0 * (double)p[c - Cs];
+      q += 8.0 * (double)p[Cl + c - Cs];
+    }
+  }
+  s = block_sum(s, scratch);
+  q = block_sum(q, scratch);
+  if (threadIdx.x == 0) {
+    const double m = (double)cpg * (double)S;
+    const double mu = s / m;
+    double var = q / m - mu * mu;
+    if (var < 0.0) var = 0.0;
+    s_mean = (float)mu;
+    s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    mean[n * G + g] = s_mean;
+    rstd[n * G + g] = s_rstd;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    const int c = g * cpg + i;
+    const float a = gamma[c] * s_rstd;
+    ab[((int64_t)n * 2 + 0) * C + c] = a;
+    ab[((int64_t)n * 2 + 1) * C + c] = beta[c] - s_mean * a;
+  }
+}
+
+template <typename T, int V>
+__global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ y,
+                                      const float* __restrict__ ab, int D, int H, int W, int Cs, int Cl, int ncol,
+                                      int rows_per_slab) {
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int S = D * H * W, C = Cs + Cl, ncs = Cs / V;
+  const int h = H >> 1, w = W >> 1;
+  const int r0 = slab * rows_per_slab;
+  const int r1 = min(r0 + rows_per_slab, S);
+  float a[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    a[i] = ab[((int64_t)n * 2 + 0) * C + col * V + i];
+    b[i] = ab[((int64_t)n * 2 + 1) * C + col * V + i];
+  }
+  const bool from_skip = col < ncs;
+  const T* sbase = skip + (int64_t)n * S * Cs + col * V;
+  const T* lbase = low + (int64_t)n * (S >> 3) * Cl + (col - ncs) * V;
+  T* ybase = y + (int64_t)n * S * C + col * V;
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float v[V];
+    if (from_skip) {
+      load_vec<T, V>(sbase + (int64_t)r * Cs, v);
+    } else {
+      const int x = r % W, t = r / W, yy = t % H, z = t / H;
+      const int rl = ((z >> 1) * h + (yy >> 1)) * w + (x >> 1);
+      load_vec<T, V>(lbase + (int64_t)rl * Cl, v);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = fmaf(v[i], a[i], b[i]);
+    store_vec<T, V>(ybase + (int64_t)r * C, v);
+  }
+}
+
+// backward stage 1 on the virtual concat: partial[n][slab][{sum dy, sum dy*x}][C]
+template <typename T, int V>
+__global__ void upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T* __restrict__ low,
+                                            const T* __restrict__ dy, float* __restrict__ partial, int D, int H, int W,
+                                            int Cs, int Cl, int ncol, int rows_per_slab, int nslab) {
+  extern __shared__ float sm[];
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int S = D * H * W, C = Cs + Cl, ncs = Cs / V;
+  const int h = H >> 1, w = W >> 1;
+  const int r0 = slab * rows_per_slab;
+  const int r1 = min(r0 + rows_per_slab, S);
+  float acc[2 * V];
+#pragma unroll
+  for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
+  const bool active = col < ncol;
+  if (active) {
+    const bool from_skip = col < ncs;
+    const T* sbase = skip + (int64_t)n * S * Cs + col * V;
+    const T* lbase = low + (int64_t)n * (S >> 3) * Cl + (col - ncs) * V;
+    const T* gbase = dy + (int64_t)n * S * C + col * V;
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float xv[V], gv[V];
+      if (from_skip) {
+        load_vec<T, V>(sbase + (int64_t)r * Cs, xv);
+      } else {
+        const int x = r % W, t = r / W, yy = t % H, z = t / H;
+        load_vec<T, V>(lbase + (int64_t)(((z >> 1) * h + (yy >> 1)) * w + (x >> 1)) * Cl, xv);
+      }
+      load_vec<T, V>(gbase + (int64_t)r * C, gv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        acc[i] += gv[i];
+        acc[V + i] += gv[i] * xv[i];
+      }
+    }
+  }
+  float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
+  reduce_over_y<2 * V>(acc, sm, [&](int i, float total) {
+    if (active) out[(i / V) * C + col * V + (i % V)] = total;
+  });
+}
+
+// backward stage 3a: dskip = (A*dy + B*skip + Cc) * skip_act'(skip) for the first Cs concat channels
+template <typename T, int V>
+__global__ void upcat_gn_bwd_skip_kernel(const T* __restrict__ skip, const T* __restrict__ dy,
+                                         const float* __restrict__ coef, T* __restrict__ dskip, int64_t S, int Cs, int C,
+                                         int ncol, int64_t rows_per_slab, int act, float act_param) {
+  const int col = blockIdx.z * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int64_t r0 = (int64_t)slab * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > S) r1 = S;
+  float A[V], B[V], Cc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    A[i] = coef[((int64_t)n * 3 + 0) * C + col * V + i];
+    B[i] = coef[((int64_t)n * 3 + 1) * C + col * V + i];
+    Cc[i] = coef[((int64_t)n * 3 + 2) * C + col * V + i];
+  }
+  const T* xb = skip + (int64_t)n * S * Cs + col * V;
+  const T* gb = dy + (int64_t)n * S * C + col * V;
+  T* ob = dskip + (int64_t)n * S * Cs + col * V;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float xv[V], gv[V];
+    load_vec<T, V>(xb + r * Cs, xv);
+    load_vec<T, V>(gb + r * C, gv);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], act, act_param);
+    store_vec<T, V>(ob + r * Cs, xv);
+  }
+}
+
+// backward stage 3b: dlow = (A * sum_8 dy + 8 * (B*low + Cc)) * low_act'(low) for the last Cl concat channels
+template <typename T, int V>
+__global__ void upcat_gn_bwd_low_kernel(const T* __restrict__ low, const T* __restrict__ dy,
+                                        const float* __restrict__ coef, T* __restrict__ dlow, int N, int D, int H, int W,
+                                        int Cs, int Cl, int act, float act_param) {
+  const int C = Cs + Cl, ncl = Cl / V;
+  const int d = D >> 1, h = H >> 1, w = W >> 1;
+  const int64_t total = (int64_t)N * d * h * w * ncl;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % ncl);
+    int64_t t = i / ncl;
+    const int x = (int)(t % w); t /= w;
+    const int yy = (int)(t % h); t /= h;
+    const int z = (int)(t % d);
+    const int n = (int)(t / d);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t row = (((int64_t)n * D + 2 * z + (k >> 2)) * H + 2 * yy + ((k >> 1) & 1)) * W + 2 * x + (k & 1);
+      float g[V];
+      load_vec<T, V>(dy + row * C + Cs + cv * V, g);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += g[j];
+    }
+    float xv[V];
+    load_vec<T, V>(low + i * V, xv);
+    const float* cf = coef + (int64_t)n * 3 * C + Cs + cv * V;
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      xv[j] = fmaf(cf[j], acc[j], 8.f * fmaf(cf[C + j], xv[j], cf[2 * C + j])) * act_grad_from_out(xv[j], act, act_param);
+    store_vec<T, V>(dlow + i * V, xv);
   }
 }
 
@@ -399,7 +603,8 @@ extern "C" int mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspa
   MEDNET_DISPATCH_TV(p->dtype, pl.V, {
     gn_bwd_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy, coef,
                                                            (T*)p->dx, (T*)p->dresidual, p->S, p->C, pl.ncol,
-                                                           pl.rows_per_slab, p->act, p->act_param);
+                                                           pl.rows_per_slab, p->act, p->act_param, p->in_act,
+                                                           p->in_act_param);
   });
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
@@ -427,5 +632,149 @@ extern "C" int mednet_act_bwd(const mednet_act_bwd_params* p, mednet_stream_t st
                                                                    p->act, p->act_param);
   });
   MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm over the virtual concat
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct UpcatPlan {
+  int V;
+  SlabPlan pa, pb, pc;       // stats over skip, stats over low, apply/backward over the concat grid
+  size_t pa_bytes, pb_bytes;
+};
+bool upcat_geometry_ok(int N, int D, int H, int W, int d, int h, int w, int Cs, int Cl, int G) {
+  return N > 0 && N <= 65535 && Cs > 0 && Cl > 0 && G > 0 && (Cs + Cl) % G == 0 && d > 0 && h > 0 && w > 0 &&
+         D == 2 * d && H == 2 * h && W == 2 * w && (int64_t)D * H * W < ((int64_t)1 << 31);
+}
+UpcatPlan upcat_plan(int N, int D, int H, int W, int Cs, int Cl, int dtype) {
+  UpcatPlan u;
+  const int eb = dtype_bytes(dtype);
+  const int va = pick_vec(Cs, eb), vb = pick_vec(Cl, eb);
+  u.V = va < vb ? va : vb;
+  const int64_t S = (int64_t)D * H * W;
+  u.pa = make_plan(N, S, Cs, eb);
+  u.pb = make_plan(N, S / 8, Cl, eb);
+  u.pc = make_plan(N, S, Cs + Cl, eb, u.V);
+  u.pa_bytes = align_up((size_t)N * u.pa.nslab * 2 * Cs * sizeof(float), 256);
+  u.pb_bytes = align_up((size_t)N * u.pb.nslab * 2 * Cl * sizeof(float), 256);
+  return u;
+}
+}  // namespace
+
+extern "C" size_t mednet_upcat_groupnorm_fwd_workspace_bytes(const mednet_upcat_gn_fwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || !upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G)) return 0;
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  return u.pa_bytes + u.pb_bytes + align_up((size_t)p->N * 2 * (p->Cs + p->Cl) * sizeof(float), 256);
+}
+
+extern "C" int mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
+                                          mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->skip && p->low && p->gamma && p->beta && p->y && p->mean && p->rstd, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_upcat_groupnorm_fwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  const int64_t S = (int64_t)p->D * p->H * p->W;
+  const int C = p->Cs + p->Cl;
+  float* pa = (float*)workspace;
+  float* pb = (float*)((char*)workspace + u.pa_bytes);
+  float* ab = (float*)((char*)workspace + u.pa_bytes + u.pb_bytes);
+  {
+    const SlabPlan& pl = u.pa;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->skip, pa, S, p->Cs, pl.ncol, pl.rows_per_slab,
+                                                              pl.nslab);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  {
+    const SlabPlan& pl = u.pb;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->low, pb, S / 8, p->Cl, pl.ncol, pl.rows_per_slab,
+                                                              pl.nslab);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  upcat_gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(pa, pb, p->gamma, p->beta, p->mean, p->rstd, ab, S,
+                                                                        p->Cs, p->Cl, p->G, u.pa.nslab, u.pb.nslab, p->eps);
+  MEDNET_LAUNCH_CHECK();
+  {
+    const SlabPlan& pl = u.pc;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      upcat_gn_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->skip, (const T*)p->low, (T*)p->y, ab, p->D, p->H,
+                                                               p->W, p->Cs, p->Cl, pl.ncol, (int)pl.rows_per_slab);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  (void)C;
+  return MEDNET_OK;
+}
+
+extern "C" size_t mednet_upcat_groupnorm_bwd_workspace_bytes(const mednet_upcat_gn_bwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || !upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G)) return 0;
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  const int C = p->Cs + p->Cl;
+  return align_up((size_t)p->N * u.pc.nslab * 2 * C * sizeof(float), 256) + align_up((size_t)p->N * 3 * C * sizeof(float), 256) +
+         align_up((size_t)p->N * 2 * C * sizeof(float), 256);
+}
+
+extern "C" int mednet_upcat_groupnorm_bwd(const mednet_upcat_gn_bwd_params* p, void* workspace, size_t workspace_bytes,
+                                          mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->skip && p->low && p->dy && p->gamma && p->mean && p->rstd && p->dskip && p->dlow && p->dgamma &&
+                     p->dbeta, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_upcat_groupnorm_bwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  const int64_t S = (int64_t)p->D * p->H * p->W;
+  const int C = p->Cs + p->Cl;
+  char* ws = (char*)workspace;
+  float* partial = (float*)ws;
+  ws += align_up((size_t)p->N * u.pc.nslab * 2 * C * sizeof(float), 256);
+  float* coef = (float*)ws;
+  ws += align_up((size_t)p->N * 3 * C * sizeof(float), 256);
+  float* dgb = (float*)ws;
+  {
+    const SlabPlan& pl = u.pc;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      upcat_gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->skip, (const T*)p->low, (const T*)p->dy,
+                                                                        partial, p->D, p->H, p->W, p->Cs, p->Cl, pl.ncol,
+                                                                        (int)pl.rows_per_slab, pl.nslab);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  gn_bwd_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(partial, p->gamma, p->mean, p->rstd, coef, dgb, S, C,
+                                                                      p->G, u.pc.nslab);
+  MEDNET_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(dgb, p->dgamma, p->dbeta, p->N, C, p->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  {
+    SlabPlan pl = make_plan(p->N, S, p->Cs, dtype_bytes(p->dtype), u.V);
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      upcat_gn_bwd_skip_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->skip, (const T*)p->dy, coef, (T*)p->dskip, S,
+                                                                  p->Cs, C, pl.ncol, pl.rows_per_slab, p->skip_act,
+                                                                  p->skip_act_param);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  {
+    const int64_t total = (int64_t)p->N * (S / 8) * (p->Cl / u.V);
+    MEDNET_DISPATCH_TV(p->dtype, u.V, {
+      upcat_gn_bwd_low_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->low, (const T*)p->dy, coef,
+                                                                               (T*)p->dlow, p->N, p->D, p->H, p->W, p->Cs,
+                                                                               p->Cl, p->low_act, p->low_act_param);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
   return MEDNET_OK;
 }

@@ -230,7 +230,7 @@ def k_conv1_fwd(x, w2d, bias):
     return y
 
 
-def k_conv1_bwd(x, w2d, dy, need_dx=True):
+def k_conv1_bwd(x, w2d, dy, need_dx=True, in_act=0):
     _need_cuda(x, w2d, dy)
     n, sp, cin = x.shape[0], tuple(x.shape[1:-1]), x.shape[-1]
     cout = w2d.shape[0]
@@ -239,7 +239,7 @@ def k_conv1_bwd(x, w2d, dy, need_dx=True):
     dw = torch.empty((cout, cin), dtype=torch.float32, device=x.device)
     db = torch.empty(cout, dtype=torch.float32, device=x.device)
     p = make("mednet_conv1_bwd_params", x=_ptr(x), w=_ptr(w2d), dy=_ptr(dy), dx=_ptr(dx), dw=_ptr(dw), db=_ptr(db), N=n,
-             S=s, Cin=cin, Cout=cout, dtype=_dt(x), accumulate=0)
+             S=s, Cin=cin, Cout=cout, dtype=_dt(x), accumulate=0, in_act=in_act, in_act_param=ACT_PARAM[in_act])
     ws = _ws(lib().mednet_conv1x1_bwd_workspace_bytes(_abi.C.byref(p)), x.device)
     check(lib().mednet_conv1x1_bwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv1x1_bwd")
     _count(4)
@@ -262,7 +262,7 @@ def k_gn_fwd(x, gamma, beta, groups, act=0, residual=None, eps=1e-5):
     return y, mean, rstd
 
 
-def k_gn_bwd(x, y, dy, gamma, mean, rstd, groups, act=0, want_dresidual=False):
+def k_gn_bwd(x, y, dy, gamma, mean, rstd, groups, act=0, want_dresidual=False, in_act=0):
     _need_cuda(x, dy)
     n, c = x.shape[0], x.shape[-1]
     s = x.numel() // (n * c)
@@ -272,7 +272,8 @@ def k_gn_bwd(x, y, dy, gamma, mean, rstd, groups, act=0, want_dresidual=False):
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
     p = make("mednet_gn_bwd_params", x=_ptr(x), y=_ptr(y), dy=_ptr(dy), gamma=_ptr(gamma), mean=_ptr(mean),
              rstd=_ptr(rstd), dx=_ptr(dx), dresidual=_ptr(dres), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta), N=n, S=s, C=c,
-             G=groups, dtype=_dt(x), act=act, act_param=ACT_PARAM[act], accumulate=0)
+             G=groups, dtype=_dt(x), act=act, act_param=ACT_PARAM[act], accumulate=0, in_act=in_act,
+             in_act_param=ACT_PARAM[in_act])
     ws = _ws(lib().mednet_groupnorm_bwd_workspace_bytes(_abi.C.byref(p)), x.device)
     check(lib().mednet_groupnorm_bwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "groupnorm_bwd")
     _count(4)
@@ -310,11 +311,12 @@ def k_pool_fwd(x):
     return y, idx
 
 
-def k_pool_bwd(dy, idx, in_shape):
+def k_pool_bwd(dy, idx, in_shape, y=None, in_act=0):
     _need_cuda(dy, idx)
     n, d, h, w, c = in_shape
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
-    p = make("mednet_pool_bwd_params", dy=_ptr(dy), idx=_ptr(idx), dx=_ptr(dx), N=n, D=d, H=h, W=w, C=c, dtype=_dt(dy))
+    p = make("mednet_pool_bwd_params", dy=_ptr(dy), idx=_ptr(idx), dx=_ptr(dx), N=n, D=d, H=h, W=w, C=c, dtype=_dt(dy),
+             y=_ptr(y), in_act=in_act, in_act_param=ACT_PARAM[in_act])
     check(lib().mednet_maxpool3d_bwd(_abi.C.byref(p), _stream()), "maxpool3d_bwd")
     _count()
     return dx
@@ -340,17 +342,56 @@ def k_upcat_fwd(skip, low):
     return out
 
 
-def k_upcat_bwd(dout, skip_shape, low_shape):
+def k_upcat_bwd(dout, skip_shape, low_shape, skip=None, low=None, skip_act=0, low_act=0):
     _need_cuda(dout)
     n, D, H, W, cs = skip_shape
     _, d, h, w, cl = low_shape
     dskip = torch.empty(skip_shape, dtype=dout.dtype, device=dout.device)
     dlow = torch.empty(low_shape, dtype=dout.dtype, device=dout.device)
     p = make("mednet_upcat_bwd_params", dout=_ptr(dout), dskip=_ptr(dskip), dlow=_ptr(dlow), N=n, D=D, H=H, W=W, d=d,
-             h=h, w=w, Cs=cs, Cl=cl, dtype=_dt(dout))
+             h=h, w=w, Cs=cs, Cl=cl, dtype=_dt(dout), skip=_ptr(skip), low=_ptr(low), skip_act=skip_act, low_act=low_act,
+             skip_act_param=ACT_PARAM[skip_act], low_act_param=ACT_PARAM[low_act])
     check(lib().mednet_upsample_concat_bwd(_abi.C.byref(p), _stream()), "upsample_concat_bwd")
     _count(2)
     return dskip, dlow
+
+
+def upcat_gn_supported(skip, low):
+    """Exact 2x nearest upsampling (the only case the fused virtual-concat GroupNorm handles)."""
+    return tuple(skip.shape[1:4]) == tuple(2 * v for v in low.shape[1:4]) and skip.numel() // skip.shape[0] < 2 ** 31
+
+
+def k_upcat_gn_fwd(skip, low, gamma, beta, groups, eps=1e-5):
+    _need_cuda(skip, low, gamma, beta)
+    n, D, H, W, cs = skip.shape
+    _, d, h, w, cl = low.shape
+    y = torch.empty((n, D, H, W, cs + cl), dtype=low.dtype, device=low.device)
+    mean = torch.empty((n, groups), dtype=torch.float32, device=low.device)
+    rstd = torch.empty((n, groups), dtype=torch.float32, device=low.device)
+    p = make("mednet_upcat_gn_fwd_params", skip=_ptr(skip), low=_ptr(low), gamma=_ptr(gamma), beta=_ptr(beta), y=_ptr(y),
+             mean=_ptr(mean), rstd=_ptr(rstd), N=n, D=D, H=H, W=W, d=d, h=h, w=w, Cs=cs, Cl=cl, G=groups, dtype=_dt(low),
+             eps=eps)
+    ws = _ws(lib().mednet_upcat_groupnorm_fwd_workspace_bytes(_abi.C.byref(p)), low.device)
+    check(lib().mednet_upcat_groupnorm_fwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "upcat_groupnorm_fwd")
+    _count(4)
+    return y, mean, rstd
+
+
+def k_upcat_gn_bwd(skip, low, dy, gamma, mean, rstd, groups, skip_act=0, low_act=0):
+    _need_cuda(skip, low, dy)
+    n, D, H, W, cs = skip.shape
+    _, d, h, w, cl = low.shape
+    dskip, dlow = torch.empty_like(skip), torch.empty_like(low)
+    dgamma = torch.empty(cs + cl, dtype=torch.float32, device=low.device)
+    dbeta = torch.empty(cs + cl, dtype=torch.float32, device=low.device)
+    p = make("mednet_upcat_gn_bwd_params", skip=_ptr(skip), low=_ptr(low), dy=_ptr(dy), gamma=_ptr(gamma), mean=_ptr(mean),
+             rstd=_ptr(rstd), dskip=_ptr(dskip), dlow=_ptr(dlow), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta), N=n, D=D, H=H,
+             W=W, d=d, h=h, w=w, Cs=cs, Cl=cl, G=groups, dtype=_dt(low), accumulate=0, skip_act=skip_act, low_act=low_act,
+             skip_act_param=ACT_PARAM[skip_act], low_act_param=ACT_PARAM[low_act])
+    ws = _ws(lib().mednet_upcat_groupnorm_bwd_workspace_bytes(_abi.C.byref(p)), low.device)
+    check(lib().mednet_upcat_groupnorm_bwd(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "upcat_groupnorm_bwd")
+    _count(5)
+    return dskip, dlow, dgamma, dbeta
 
 
 def _logit_view(t):
@@ -498,7 +539,9 @@ class Conv3x3Fn(torch.autograd.Function):
     ref: midasmednet/unet/components.py:8-9 (+ :35-40 for the fused non-linearity)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, addend, act, impl):
+    def forward(ctx, x, weight, bias, addend, act, impl, defer_act=False):
+        """defer_act: the activation derivative is applied by the CONSUMERS of y (their `in_act`, see
+        include/mednet_b200.h "Deferred activation derivative"); backward then receives d(pre-activation)."""
         x = _c(x)
         cout, cin = weight.shape[0], weight.shape[1]
         sp = tuple(x.shape[1:4])
@@ -507,8 +550,9 @@ class Conv3x3Fn(torch.autograd.Function):
         add = _c(addend) if addend is not None else None
         y = k_conv3(x, wp, cout, sp, 0, impl_id, bias=bias.detach().float() if bias is not None else None,
                     addend=add, act=act)
-        ctx.save_for_backward(x, weight, y if act else None)
-        ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = act, impl, bias is not None, addend is not None
+        bwd_act = 0 if defer_act else act
+        ctx.save_for_backward(x, weight, y if bwd_act else None)
+        ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = bwd_act, impl, bias is not None, addend is not None
         return y
 
     @staticmethod
@@ -525,7 +569,7 @@ class Conv3x3Fn(torch.autograd.Function):
             dx = k_conv3(dpre, wp, cin, sp, 0, impl_id)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = k_wgrad(dpre, x, 0, "simt" if ctx.impl == "simt" else "auto", want_bias=ctx.has_bias)
-        return dx, dw, db, (dpre if ctx.has_addend else None), None, None
+        return dx, dw, db, (dpre if ctx.has_addend else None), None, None, None
 
 
 class ConvTranspose3x3Fn(torch.autograd.Function):
@@ -565,20 +609,41 @@ class GroupNormActFn(torch.autograd.Function):
     """GroupNorm (+ residual add) (+ activation).  ref: components.py:57, :36-40, :177-178."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, act, residual):
+    def forward(ctx, x, gamma, beta, groups, act, residual, in_act=0):
         x = _c(x)
         res = _c(residual) if residual is not None else None
         g, b = gamma.detach().float(), beta.detach().float()
         y, mean, rstd = k_gn_fwd(x, g, b, groups, act, res)
         ctx.save_for_backward(x, y if act else None, g, mean, rstd)
-        ctx.groups, ctx.act, ctx.has_res = groups, act, residual is not None
+        ctx.groups, ctx.act, ctx.has_res, ctx.in_act = groups, act, residual is not None, in_act
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, g, mean, rstd = ctx.saved_tensors
-        dx, dgamma, dbeta, dres = k_gn_bwd(x, y, _c(dy), g, mean, rstd, ctx.groups, ctx.act, ctx.has_res)
-        return dx, dgamma, dbeta, None, None, dres
+        dx, dgamma, dbeta, dres = k_gn_bwd(x, y, _c(dy), g, mean, rstd, ctx.groups, ctx.act, ctx.has_res, ctx.in_act)
+        return dx, dgamma, dbeta, None, None, dres, None
+
+
+class UpcatGroupNormFn(torch.autograd.Function):
+    """GroupNorm(cat((skip, nearest_up2(low)), 1)) without materialising the concat.
+    ref: components.py:277-280 (interpolate + cat) followed by :57 (the 'g' of the decoder's first 'gcr' layer)."""
+
+    @staticmethod
+    def forward(ctx, skip, low, gamma, beta, groups, skip_act, low_act):
+        skip, low = _c(skip), _c(low)
+        g, b = gamma.detach().float(), beta.detach().float()
+        y, mean, rstd = k_upcat_gn_fwd(skip, low, g, b, groups)
+        ctx.save_for_backward(skip, low, g, mean, rstd)
+        ctx.cfg = (groups, skip_act, low_act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        skip, low, g, mean, rstd = ctx.saved_tensors
+        groups, skip_act, low_act = ctx.cfg
+        dskip, dlow, dgamma, dbeta = k_upcat_gn_bwd(skip, low, _c(dy), g, mean, rstd, groups, skip_act, low_act)
+        return dskip, dlow, dgamma, dbeta, None, None, None
 
 
 class ActFn(torch.autograd.Function):
@@ -599,51 +664,54 @@ class MaxPoolFn(torch.autograd.Function):
     """MaxPool3d(2).  ref: components.py:210,224."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, in_act=0):
         x = _c(x)
         y, idx = k_pool_fwd(x)
-        ctx.save_for_backward(idx)
-        ctx.in_shape = tuple(x.shape)
+        ctx.save_for_backward(idx, y if in_act else None)    # y is kept alive by its consumer anyway
+        ctx.in_shape, ctx.in_act = tuple(x.shape), in_act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (idx,) = ctx.saved_tensors
-        return k_pool_bwd(_c(dy), idx, ctx.in_shape)
+        idx, y = ctx.saved_tensors
+        return k_pool_bwd(_c(dy), idx, ctx.in_shape, y, ctx.in_act), None
 
 
 class UpsampleConcatFn(torch.autograd.Function):
     """F.interpolate(x, size=skip.shape[2:], 'nearest') + cat((skip, x), 1).  ref: components.py:277-280."""
 
     @staticmethod
-    def forward(ctx, skip, low):
+    def forward(ctx, skip, low, skip_act=0, low_act=0):
         skip, low = _c(skip), _c(low)
         ctx.shapes = (tuple(skip.shape), tuple(low.shape))
+        ctx.acts = (skip_act, low_act)
+        ctx.save_for_backward(skip if skip_act else None, low if low_act else None)
         return k_upcat_fwd(skip, low)
 
     @staticmethod
     def backward(ctx, dout):
-        dskip, dlow = k_upcat_bwd(_c(dout), *ctx.shapes)
-        return dskip, dlow
+        skip, low = ctx.saved_tensors
+        dskip, dlow = k_upcat_bwd(_c(dout), *ctx.shapes, skip, low, *ctx.acts)
+        return dskip, dlow, None, None
 
 
 class Conv1x1Fn(torch.autograd.Function):
     """Final 1x1x1 conv with bias: NDHWC activations -> NCDHW fp32 logits.  ref: model.py:77,102."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, in_act=0):
         x = _c(x)
         w2 = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
         y = k_conv1_fwd(x, w2, bias.detach().float().contiguous())
         ctx.save_for_backward(x, w2)
-        ctx.wshape = tuple(weight.shape)
+        ctx.wshape, ctx.in_act = tuple(weight.shape), in_act
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w2 = ctx.saved_tensors
-        dx, dw, db = k_conv1_bwd(x, w2, dy.contiguous().float(), need_dx=ctx.needs_input_grad[0])
-        return dx, dw.reshape(ctx.wshape), db
+        dx, dw, db = k_conv1_bwd(x, w2, dy.contiguous().float(), need_dx=ctx.needs_input_grad[0], in_act=ctx.in_act)
+        return dx, dw.reshape(ctx.wshape), db, None
 
 
 class ToChannelsLastFn(torch.autograd.Function):

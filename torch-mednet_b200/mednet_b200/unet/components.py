@@ -144,21 +144,43 @@ class SingleConv(nn.Module):
                 i += 1
         self._plan = plan
 
-    def run(self, x, residual=None, final_act=0):
+    # -- deferred activation derivative (include/mednet_b200.h): a layer that ENDS in conv+activation can leave
+    #    act'(y) to the consumers of y; a layer that STARTS with a GroupNorm can apply it for its producer.
+    @property
+    def out_act(self):
+        kind, act = self._plan[-1]
+        return act if kind == 'c' else 0
+
+    @property
+    def accepts_in_act(self):
+        return self._plan[0][0] == 'g'
+
+    @property
+    def starts_with_plain_groupnorm(self):
+        return self._plan[0] == ('g', 0)
+
+    def run(self, x, residual=None, final_act=0, in_act=0, defer=False, skip_first=False):
         """x: NDHWC tensor.  ``residual``/``final_act`` fuse `out += residual; act(out)` (components.py:177-178)
-        into the last kernel of the layer."""
+        into the last kernel of the layer.  ``in_act``: activation of x's producer whose derivative this layer's
+        first op applies in backward; ``defer``: leave this layer's trailing conv activation derivative to the
+        consumers; ``skip_first``: the first op (a GroupNorm) was already applied by a fused producer."""
         last = len(self._plan) - 1
+        if in_act and not self.accepts_in_act:
+            raise RuntimeError("in_act needs a layer that starts with GroupNorm")
         for i, (kind, act) in enumerate(self._plan):
+            if i == 0 and skip_first:
+                continue
             fuse = (i == last) and (residual is not None or final_act)
             if fuse and act:
                 raise RuntimeError("a residual join cannot follow a layer that already ends in a non-linearity")
             if kind == 'c':
                 x = ops.Conv3x3Fn.apply(x, self.conv.weight, self.conv.bias, residual if fuse else None,
-                                        final_act if fuse else act, self.cfg.conv_impl)
+                                        final_act if fuse else act, self.cfg.conv_impl,
+                                        bool(defer and i == last and not fuse and act))
             elif kind == 'g':
                 gn = self.groupnorm
                 x = ops.GroupNormActFn.apply(x, gn.weight, gn.bias, gn.num_groups, final_act if fuse else act,
-                                             residual if fuse else None)
+                                             residual if fuse else None, in_act if i == 0 else 0)
             else:
                 x = ops.ActFn.apply(x, act)
         return x
@@ -187,8 +209,18 @@ class DoubleConv(nn.Module):
         self.add_module('SingleConv2', SingleConv(conv2_in_channels, conv2_out_channels, kernel_size, order, num_groups,
                                                    cfg=self.cfg))
 
-    def run(self, x):
-        return self.SingleConv2.run(self.SingleConv1.run(x))
+    @property
+    def out_act(self):
+        return self.SingleConv2.out_act
+
+    @property
+    def accepts_in_act(self):
+        return self.SingleConv1.accepts_in_act
+
+    def run(self, x, in_act=0, defer=False, skip_first=False):
+        inner = self.SingleConv1.out_act if self.SingleConv2.accepts_in_act else 0
+        h = self.SingleConv1.run(x, in_act=in_act, defer=bool(inner), skip_first=skip_first)
+        return self.SingleConv2.run(h, in_act=inner, defer=defer)
 
     def forward(self, x):
         return from_ndhwc(self.run(to_ndhwc(x, self.cfg)))
@@ -218,7 +250,11 @@ class ExtResNetBlock(nn.Module):
             self._act = ops.ACT['r']
         self.non_linearity = nn.Identity()
 
-    def run(self, x):
+    out_act = 0                  # ends in GroupNorm(+residual)+activation: nothing to defer
+    accepts_in_act = False
+
+    def run(self, x, in_act=0, defer=False):
+        assert not in_act and not defer
         out = self.conv1.run(x)
         residual = out
         out = self.conv2.run(out)
@@ -229,8 +265,8 @@ class ExtResNetBlock(nn.Module):
 
 
 class _MaxPool(nn.Module):
-    def forward(self, x):
-        return ops.MaxPoolFn.apply(x)
+    def forward(self, x, in_act=0):
+        return ops.MaxPoolFn.apply(x, in_act)
 
 
 class Encoder(nn.Module):
@@ -250,9 +286,16 @@ class Encoder(nn.Module):
         self.basic_module = basic_module(in_channels, out_channels, encoder=True, kernel_size=conv_kernel_size,
                                          order=conv_layer_order, num_groups=num_groups, cfg=self.cfg)
 
-    def run(self, x):
+    def accepts_in_act(self):
+        return self.pooling is not None or self.basic_module.accepts_in_act
+
+    def run(self, x, in_act=0, defer=False):
+        """in_act: activation of x's producer (derivative applied by the pool / first GroupNorm in backward)."""
         if self.pooling is not None:
-            x = self.pooling(x)
+            x = self.pooling(x, in_act)
+            in_act = 0
+        if in_act or defer:
+            return self.basic_module.run(x, in_act=in_act, defer=defer)
         return self.basic_module.run(x)
 
     def forward(self, x):
@@ -277,12 +320,26 @@ class Decoder(nn.Module):
         self.basic_module = basic_module(in_channels, out_channels, encoder=False, kernel_size=kernel_size,
                                          order=conv_layer_order, num_groups=num_groups, cfg=self.cfg)
 
-    def run(self, encoder_features, x):
+    def accepts_in_act(self):
+        return self.upsample is None
+
+    def run(self, encoder_features, x, skip_act=0, x_act=0, defer=False):
+        """skip_act / x_act: activations of the producers of the two inputs whose derivatives are deferred to
+        this decoder's join; defer: leave the trailing conv activation derivative to the consumer."""
         if self.upsample is None:
-            x = ops.UpsampleConcatFn.apply(encoder_features, x)
+            first = self.basic_module.SingleConv1 if isinstance(self.basic_module, DoubleConv) else None
+            if first is not None and first.starts_with_plain_groupnorm and ops.upcat_gn_supported(encoder_features, x):
+                # GroupNorm over the virtual concat: the (N, Cs+Cl, S) concat tensor is never written
+                gn = first.groupnorm
+                xn = ops.UpcatGroupNormFn.apply(encoder_features, x, gn.weight, gn.bias, gn.num_groups, skip_act, x_act)
+                return self.basic_module.run(xn, defer=defer, skip_first=True)
+            x = ops.UpsampleConcatFn.apply(encoder_features, x, skip_act, x_act)
         else:
+            assert not skip_act and not x_act
             x = ops.ConvTranspose3x3Fn.apply(x, self.upsample.weight, self.upsample.bias, encoder_features,
                                              self.cfg.conv_impl)
+        if defer:
+            return self.basic_module.run(x, defer=True)
         return self.basic_module.run(x)
 
     def forward(self, encoder_features, x):

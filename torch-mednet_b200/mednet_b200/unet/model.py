@@ -51,15 +51,32 @@ class _UNetBase(LightningModule):
         return self
 
     def _run(self, x):
+        """Encoder/decoder walk of model.py:84-103.  When every block ends in conv+activation and every consumer of
+        a block output (pool, upsample/concat join, final 1x1x1 conv) can apply the activation derivative itself, the
+        convolutions skip their separate activation-backward pass (`defer`, see include/mednet_b200.h)."""
         x = to_ndhwc(x, self.cfg)
-        encoders_features = []
+        blocks = [e.basic_module for e in self.encoders] + [d.basic_module for d in self.decoders]
+        defer = torch.is_grad_enabled() and all(getattr(b, 'out_act', 0) for b in blocks) and \
+            all(e.accepts_in_act() for e in self.encoders[1:]) and all(d.accepts_in_act() for d in self.decoders)
+        if not defer:
+            encoders_features = []
+            for encoder in self.encoders:
+                x = encoder.run(x)
+                encoders_features.insert(0, x)
+            encoders_features = encoders_features[1:]
+            for decoder, encoder_features in zip(self.decoders, encoders_features):
+                x = decoder.run(encoder_features, x)
+            return ops.Conv1x1Fn.apply(x, self.final_conv.weight, self.final_conv.bias)
+        feats, acts, act = [], [], 0
         for encoder in self.encoders:
-            x = encoder.run(x)
-            encoders_features.insert(0, x)
-        encoders_features = encoders_features[1:]
-        for decoder, encoder_features in zip(self.decoders, encoders_features):
-            x = decoder.run(encoder_features, x)
-        return ops.Conv1x1Fn.apply(x, self.final_conv.weight, self.final_conv.bias)
+            x = encoder.run(x, in_act=act, defer=True)
+            act = encoder.basic_module.out_act
+            feats.insert(0, x)
+            acts.insert(0, act)
+        for decoder, skip, skip_act in zip(self.decoders, feats[1:], acts[1:]):
+            x = decoder.run(skip, x, skip_act=skip_act, x_act=act, defer=True)
+            act = decoder.basic_module.out_act
+        return ops.Conv1x1Fn.apply(x, self.final_conv.weight, self.final_conv.bias, act)
 
 
 class UNet3D(_UNetBase):
