@@ -66,7 +66,8 @@ def test_conv3_simt_fp32_fwd_bwd(cin, cout, shape, act):
 
 
 @pytest.mark.parametrize("cin,cout,shape", [(1, 32, (5, 9, 70)), (1, 8, (3, 4, 5)), (2, 16, (4, 6, 7)), (4, 64, (2, 5, 66)),
-                                            (1, 24, (4, 4, 9))])
+                                            (1, 24, (4, 4, 9)), (1, 16, (3, 5, 6)), (1, 64, (2, 3, 133)), (3, 16, (3, 4, 3)),
+                                            (1, 32, (3, 3, 2))])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_first_layer_small_channel_kernels(cin, cout, shape, dtype):
     """in_channels = 1 layers (segmentation.py:30-31): few-input-channel fprop, few-output-channel dgrad and the

@@ -76,6 +76,23 @@ static inline int pick_vec(int64_t c, int elem_bytes) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-thread asynchronous global->shared copies (LDGSTS).  Used as a PRIVATE software pipeline: a thread copies
+// the operands of its next few loop iterations into its own shared-memory slots, so many loads are in flight
+// without holding registers, and reads back only what it wrote itself (no block barrier needed).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // activations (ref: midasmednet/unet/components.py:35-40)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float act_apply(float x, int act, float a) {

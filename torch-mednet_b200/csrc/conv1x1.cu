@@ -131,6 +131,7 @@ __global__ void conv1_dx_kernel(const float* __restrict__ dy, const float* __res
 // partial[b][co][ci] = sum over the block's rows of dy[.,co] * x[.,ci]
 // block = (Cin_t, R): thread (tx,ty) owns input channel tx and rows ty, ty+R, ...
 constexpr int DW_MAX_CO = 16;
+constexpr int DW_STAGES = 6;   // rows in flight per thread in the vectorised dw/dx kernel
 template <typename T>
 __global__ void conv1_dw_partial_kernel(const T* __restrict__ x, const float* __restrict__ dy,
                                         float* __restrict__ partial, int64_t N, int64_t S, int Cin, int Cout,
@@ -193,51 +194,65 @@ __global__ void __launch_bounds__(256) conv1_dw_vec_kernel(const T* __restrict__
     for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
   const T* xb = x + (int64_t)n * S * Cin + tx * V;
   const float* dyb = dy + ((int64_t)n * Cout + co0) * S;
+  // Private LDGSTS pipeline: the x vector (16 B) and the CO_T dy scalars of this thread's next DW_STAGES - 1 rows are
+  // in flight in its own shared-memory slots (the accumulators keep the register file full, so loads cannot be
+  // batched in registers).
+  uint8_t* pipe = reinterpret_cast<uint8_t*>(sm) + (size_t)8 * ncol * CO_T * V * sizeof(float);
+  uint8_t* xslot = pipe + (size_t)threadIdx.x * 16;                                    // [stage][256] x 16 B
+  float* gslot = reinterpret_cast<float*>(pipe + (size_t)DW_STAGES * 256 * 16) + threadIdx.x * CO_T;   // [stage][256][CO_T]
+  const int64_t nrows = s1 > s0 + ty ? (s1 - s0 - ty + R - 1) / R : 0;
+  auto issue = [&](int64_t k) {
+    if (k < nrows) {
+      const int64_t srow = s0 + ty + k * R;
+      const int st = (int)(k % DW_STAGES);
+      cp_async16(xslot + (size_t)st * 256 * 16, xb + srow * Cin);
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+        if (j < nco) cp_async4(gslot + (size_t)st * 256 * CO_T + j, dyb + (int64_t)j * S + srow);
+    }
+    cp_async_commit();
+  };
+  for (int k = 0; k < DW_STAGES - 1; ++k) issue(k);
+  float wr[CO_T][V];
+  T* dxb = nullptr;
   if (dx != nullptr) {
     // fused input gradient (single pass: Cout <= CO_T): x and dy are read ONCE for dx, dw and db;
     // dx = (sum_co dy[co] * w[co][ci]) * in_act'(x)
-    float wr[CO_T][V];
 #pragma unroll
     for (int j = 0; j < CO_T; ++j)
 #pragma unroll
       for (int i = 0; i < V; ++i) wr[j][i] = j < nco ? w[(co0 + j) * Cin + tx * V + i] : 0.f;
-    T* dxb = dx + (int64_t)n * S * Cin + tx * V;
-    for (int64_t s = s0 + ty; s < s1; s += R) {
-      float xv[V], o[V];
-      load_vec<T, V>(xb + s * Cin, xv);
+    dxb = dx + (int64_t)n * S * Cin + tx * V;
+  }
+  for (int64_t k = 0; k < nrows; ++k) {
+    issue(k + DW_STAGES - 1);
+    cp_async_wait<DW_STAGES - 1>();
+    const int st = (int)(k % DW_STAGES);
+    const int64_t srow = s0 + ty + k * R;
+    float xv[V], g[CO_T];
+    load_vec<T, V>(reinterpret_cast<const T*>(xslot + (size_t)st * 256 * 16), xv);
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) g[j] = j < nco ? gslot[(size_t)st * 256 * CO_T + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[j][i] = fmaf(g[j], xv[i], acc[j][i]);
+    if (dx != nullptr) {
+      float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < CO_T; ++j) {
-        if (j < nco) {
-          const float g = dyb[(int64_t)j * S + s];
+      for (int j = 0; j < CO_T; ++j)
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            acc[j][i] = fmaf(g, xv[i], acc[j][i]);
-            o[i] = fmaf(g, wr[j][i], o[i]);
-          }
-        }
-      }
+        for (int i = 0; i < V; ++i) o[i] = fmaf(g[j], wr[j][i], o[i]);
       if (in_act != MEDNET_ACT_NONE) {
 #pragma unroll
         for (int i = 0; i < V; ++i) o[i] *= act_grad_from_out(xv[i], in_act, in_act_param);
       }
-      store_vec<T, V>(dxb + s * Cin, o);
-    }
-  } else {
-    for (int64_t s = s0 + ty; s < s1; s += R) {
-      float xv[V];
-      load_vec<T, V>(xb + s * Cin, xv);
-#pragma unroll
-      for (int j = 0; j < CO_T; ++j) {
-        if (j < nco) {
-          const float g = dyb[(int64_t)j * S + s];
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[j][i] = fmaf(g, xv[i], acc[j][i]);
-        }
-      }
+      store_vec<T, V>(dxb + srow * Cin, o);
     }
   }
+  cp_async_wait<0>();
   // rows that share a warp (lane = (ty % rpw) * ncol + tx when ncol < 32)
   if (ncol < 32) {
     for (int off = ncol; off < 32; off <<= 1)
@@ -350,7 +365,8 @@ static Conv1Plan conv1_plan(int64_t N, int64_t S, int Cin, int Cout, int elem_by
   pl.ncol = Cin / pl.V;
   pl.co_t = Cout <= 4 ? 4 : (Cout <= 8 ? 8 : 16);
   pl.vec = (pl.ncol <= 16 && (pl.ncol & (pl.ncol - 1)) == 0 && pl.V * elem_bytes == 16 && N <= 65535 &&
-            (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float) <= 48 * 1024) ? 1 : 0;
+            (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float) + (size_t)DW_STAGES * 256 * (16 + 4 * pl.co_t) <= 100 * 1024)
+               ? 1 : 0;
   int64_t per = ((int64_t)sm_count_cached() * 4 + N - 1) / N;
   const int64_t maxper = S / ((256 / pl.ncol) * 8);
   if (per > maxper) per = maxper;
@@ -422,12 +438,17 @@ extern "C" int mednet_conv1x1_bwd(const mednet_conv1_bwd_params* p, void* worksp
   float* partial_b = (float*)((char*)workspace + align_up((size_t)pl.nblocks * p->Cout * p->Cin * sizeof(float), 256));
   if (pl.vec) {
     dim3 grid(pl.nblk_per_sample, (unsigned)p->N);
-    const size_t smv = (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float);
+    const size_t smv = (size_t)8 * pl.ncol * pl.co_t * pl.V * sizeof(float) + (size_t)DW_STAGES * 256 * (16 + 4 * pl.co_t);
     for (int co0 = 0; co0 < p->Cout; co0 += pl.co_t) {
 #define MEDNET_DWV(TT, VV, CT)                                                                                         \
-      conv1_dw_vec_kernel<TT, VV, CT><<<grid, 256, smv, stream>>>((const TT*)p->x, p->dy, partial, p->S, p->Cin, p->Cout, \
-                                                                  co0, pl.rows_per_block_vec, p->w,                    \
-                                                                  fuse_dx ? (TT*)p->dx : nullptr, p->in_act, p->in_act_param)
+      do {                                                                                                             \
+        cudaError_t ea = cudaFuncSetAttribute(conv1_dw_vec_kernel<TT, VV, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)smv);                                                               \
+        if (ea != cudaSuccess) return (int)ea;                                                                         \
+        conv1_dw_vec_kernel<TT, VV, CT><<<grid, 256, smv, stream>>>((const TT*)p->x, p->dy, partial, p->S, p->Cin, p->Cout, \
+                                                                    co0, pl.rows_per_block_vec, p->w,                  \
+                                                                    fuse_dx ? (TT*)p->dx : nullptr, p->in_act, p->in_act_param); \
+      } while (0)
       if (p->dtype == MEDNET_F32) {
         if (pl.co_t == 4) MEDNET_DWV(float, 4, 4); else if (pl.co_t == 8) MEDNET_DWV(float, 4, 8); else MEDNET_DWV(float, 4, 16);
       } else {

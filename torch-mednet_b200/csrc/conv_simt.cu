@@ -430,9 +430,173 @@ __global__ void __launch_bounds__(128) conv3_fewout_kernel(const T* __restrict__
   }
 }
 
+
+// few OUTPUT channels, register-tiled along w: TPV threads per group of 4 consecutive output voxels, each thread owns 8
+// input channels.  Per (kd, kh) the 6 input voxels of the group are loaded once (16 B each) and every weight vector
+// (2 x LDS.128) is reused by the 4 outputs -> 96 * NO FMAs for 6 global + 6 * NO shared loads.
+template <typename T, int TPV, int NO>
+__global__ void __launch_bounds__(128) conv3_fewout4_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                            const float* __restrict__ bias, const T* __restrict__ addend,
+                                                            T* __restrict__ y, int D, int H, int W, int act,
+                                                            float act_param) {
+  constexpr int K = 8 * TPV;
+  extern __shared__ float sw[];                       // [NO][27][K]
+  for (int i = threadIdx.x; i < NO * 27 * K; i += blockDim.x) sw[i] = to_f32<T>(w[i]);
+  __syncthreads();
+  const int sub = threadIdx.x % TPV;
+  const int WG = (W + 3) >> 2;
+  const int g = blockIdx.x * (128 / TPV) + threadIdx.x / TPV;
+  const bool valid = g < H * WG;
+  const int h = valid ? g / WG : 0, w0 = valid ? (g - h * WG) * 4 : 0;
+  const int n = blockIdx.y / D, d = blockIdx.y - n * D;
+  float acc[4][NO];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[j][o] = 0.f;
+  if (valid) {
+    for (int kd = 0; kd < 3; ++kd) {
+      const int id = d + kd - 1;
+      if (id < 0 || id >= D) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+        const T* xrow = x + ((((int64_t)n * D + id) * H + ih) * W) * K + sub * 8;
+        float xv[6][8];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int iw = w0 - 1 + i;
+          if (iw >= 0 && iw < W) {
+            load_vec<T, 8>(xrow + (int64_t)iw * K, xv[i]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) xv[i][c] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+          for (int o = 0; o < NO; ++o) {
+            const float* wr = sw + ((size_t)o * 27 + tap) * K + sub * 8;
+            const float4 w0v = *reinterpret_cast<const float4*>(wr), w1v = *reinterpret_cast<const float4*>(wr + 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float* xx = xv[j + kw];
+              float a = acc[j][o];
+              a = fmaf(xx[0], w0v.x, a); a = fmaf(xx[1], w0v.y, a); a = fmaf(xx[2], w0v.z, a); a = fmaf(xx[3], w0v.w, a);
+              a = fmaf(xx[4], w1v.x, a); a = fmaf(xx[5], w1v.y, a); a = fmaf(xx[6], w1v.z, a); a = fmaf(xx[7], w1v.w, a);
+              acc[j][o] = a;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = TPV / 2; off > 0; off >>= 1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) acc[j][o] += __shfl_xor_sync(0xffffffffu, acc[j][o], off);
+  if (valid && sub == 0) {
+    const int64_t vox0 = (((int64_t)n * D + d) * H + h) * W + w0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (w0 + j < W) {
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          float v = acc[j][o];
+          if (bias != nullptr) v += bias[o];
+          if (addend != nullptr) v += to_f32<T>(addend[(vox0 + j) * NO + o]);
+          y[(vox0 + j) * NO + o] = from_f32<T>(act_apply(v, act, act_param));
+        }
+      }
+    }
+  }
+}
+
+// weight gradient with ONE gathered channel (the in_channels = 1 first layer), register-tiled: a block stages a
+// 64-voxel w-segment of dY transposed ([Ca][64], fp32) and the 9 (kd, kh) halo rows of x; thread (ca, vg) owns output
+// channel ca and the 4*PIECES consecutive voxels of group vg, and for each halo row slides a 3-quad window over x so one
+// LDS.128 of x and one of dY feed 12 FMAs.  partial[block][ca][27].
+constexpr int WSEG = 64;
+constexpr int XS_PITCH = WSEG + 8, DYS_PITCH = WSEG + 4;
+template <typename T, int PIECES>
+__global__ void __launch_bounds__(256) wgrad_fewin1_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                           float* __restrict__ partial, int N, int D, int H, int W, int Ca) {
+  extern __shared__ float sm[];
+  float* dys = sm;                                    // [Ca][DYS_PITCH]
+  float* xs = sm + Ca * DYS_PITCH;                    // [9][XS_PITCH]: element i holds x at iw = w0 + i - 4
+  const int ca = threadIdx.x % Ca, vg = threadIdx.x / Ca;
+  const int v0 = vg * 4 * PIECES;
+  const int wchunks = (W + WSEG - 1) / WSEG;
+  const int64_t segs = (int64_t)N * D * H * wchunks;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  const int c8n = Ca / 8;
+  for (int64_t seg = blockIdx.x; seg < segs; seg += gridDim.x) {
+    int64_t t = seg;
+    const int w0 = (int)(t % wchunks) * WSEG; t /= wchunks;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    const int64_t rowbase = (((int64_t)n * D + d) * H + h) * W + w0;
+    for (int i = threadIdx.x; i < WSEG * c8n; i += 256) {
+      const int v = i / c8n, c8 = i - v * c8n;
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (w0 + v < W) load_vec<T, 8>(dy + (rowbase + v) * Ca + c8 * 8, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dys[(c8 * 8 + k) * DYS_PITCH + v] = g[k];
+    }
+    for (int i = threadIdx.x; i < 9 * XS_PITCH; i += 256) {
+      const int r = i / XS_PITCH, wv = i - r * XS_PITCH;
+      const int id = d + r / 3 - 1, ih = h + r % 3 - 1, iw = w0 + wv - 4;
+      float v = 0.f;
+      if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
+        v = to_f32<T>(x[(((int64_t)n * D + id) * H + ih) * W + iw]);
+      xs[i] = v;
+    }
+    __syncthreads();
+    const float4* gq = reinterpret_cast<const float4*>(dys + ca * DYS_PITCH + v0);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const float4* xq = reinterpret_cast<const float4*>(xs + r * XS_PITCH + v0);      // quad 0 = iw w0+v0-4 .. -1
+      float4 qp = xq[0], qc = xq[1];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < PIECES; ++p) {
+        const float4 qn = xq[p + 2];
+        const float4 g = gq[p];
+        a0 = fmaf(g.x, qp.w, fmaf(g.y, qc.x, fmaf(g.z, qc.y, fmaf(g.w, qc.z, a0))));
+        a1 = fmaf(g.x, qc.x, fmaf(g.y, qc.y, fmaf(g.z, qc.z, fmaf(g.w, qc.w, a1))));
+        a2 = fmaf(g.x, qc.y, fmaf(g.y, qc.z, fmaf(g.z, qc.w, fmaf(g.w, qn.x, a2))));
+        qp = qc;
+        qc = qn;
+      }
+      acc[r * 3 + 0] += a0;
+      acc[r * 3 + 1] += a1;
+      acc[r * 3 + 2] += a2;
+    }
+    __syncthreads();
+  }
+  // combine the voxel groups: sm reused as [TG][Ca][27]
+  const int TG = 256 / Ca;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 27; ++i) sm[((size_t)vg * Ca + ca) * 27 + i] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Ca * 27; i += 256) {
+    float a = 0.f;
+    for (int tg = 0; tg < TG; ++tg) a += sm[(size_t)tg * Ca * 27 + i];
+    partial[(int64_t)blockIdx.x * Ca * 27 + i] = a;
+  }
+}
+
 // weight gradient with few GATHERED channels (Cb <= 4): partial[block][ca][tap][cb]; a block walks 64-voxel
 // w-segments, thread (ca, tg) owns output channel ca and taps tg, tg+TG, ... (TG = 256 / Ca)
-constexpr int WSEG = 64, FEWIN_MAX_OWN = 7;
+constexpr int FEWIN_MAX_OWN = 7;
 template <typename T, int CB>
 __global__ void __launch_bounds__(256) wgrad_fewin_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                           float* __restrict__ partial, int N, int D, int H, int W, int Ca) {
@@ -561,7 +725,18 @@ static int fewin_wgrad_t(const mednet_wgrad_params* p, void* workspace, cudaStre
   float* partial = (float*)workspace;
   const size_t pbytes = align_up((size_t)blocks * p->Ca * 27 * p->Cb * sizeof(float), 256);
   const size_t smem = ((size_t)WSEG * p->Ca + 9 * (WSEG + 2) * p->Cb) * sizeof(float);
-  if (p->Cb == 1)
+  if (p->Cb == 1 && p->Ca >= 16) {
+    // chunk of WSEG / (256 / Ca) = Ca / 4 voxels per thread = PIECES quads
+    size_t sm1 = ((size_t)p->Ca * DYS_PITCH + 9 * XS_PITCH) * sizeof(float);
+    const size_t sm_red = (size_t)256 * 27 * sizeof(float);
+    if (sm1 < sm_red) sm1 = sm_red;
+    if (p->Ca == 16)
+      wgrad_fewin1_kernel<T, 1><<<blocks, 256, sm1, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+    else if (p->Ca == 32)
+      wgrad_fewin1_kernel<T, 2><<<blocks, 256, sm1, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+    else
+      wgrad_fewin1_kernel<T, 4><<<blocks, 256, sm1, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
+  } else if (p->Cb == 1)
     wgrad_fewin_kernel<T, 1><<<blocks, 256, smem, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
   else if (p->Cb == 2)
     wgrad_fewin_kernel<T, 2><<<blocks, 256, smem, st>>>((const T*)p->a, (const T*)p->b, partial, p->N, p->Da, p->Ha, p->Wa, p->Ca);
@@ -637,8 +812,25 @@ static int small_fprop_t(const mednet_conv3d_params* p, cudaStream_t st) {
 #undef MEDNET_FEWIN
   } else {
     const int TPV = p->K / 8;
-    dim3 grid(ceil_div(HW, 128 / TPV), (unsigned)(p->N * p->Do));
     const size_t smem = (size_t)p->Nout * 27 * p->K * sizeof(float);
+    if (p->Wo >= 4) {
+      dim3 grid4(ceil_div(p->Ho * ceil_div(p->Wo, 4), 128 / TPV), (unsigned)(p->N * p->Do));
+#define MEDNET_FEWOUT4(TP, NO)                                                                                              \
+      conv3_fewout4_kernel<T, TP, NO><<<grid4, 128, smem, st>>>((const T*)p->x, (const T*)p->w, p->bias, (const T*)p->addend, \
+                                                                (T*)p->y, p->Do, p->Ho, p->Wo, p->act, p->act_param)
+#define MEDNET_FEWOUT4_NO(TP)                                                                          \
+      do {                                                                                             \
+        if (p->Nout == 1) MEDNET_FEWOUT4(TP, 1); else if (p->Nout == 2) MEDNET_FEWOUT4(TP, 2);         \
+        else if (p->Nout == 3) MEDNET_FEWOUT4(TP, 3); else MEDNET_FEWOUT4(TP, 4);                      \
+      } while (0)
+      if (TPV == 1) MEDNET_FEWOUT4_NO(1); else if (TPV == 2) MEDNET_FEWOUT4_NO(2); else if (TPV == 4) MEDNET_FEWOUT4_NO(4);
+      else MEDNET_FEWOUT4_NO(8);
+#undef MEDNET_FEWOUT4_NO
+#undef MEDNET_FEWOUT4
+      MEDNET_LAUNCH_CHECK();
+      return MEDNET_OK;
+    }
+    dim3 grid(ceil_div(HW, 128 / TPV), (unsigned)(p->N * p->Do));
 #define MEDNET_FEWOUT(TP)                                                                                             \
     conv3_fewout_kernel<T, TP><<<grid, 128, smem, st>>>((const T*)p->x, (const T*)p->w, p->bias, (const T*)p->addend, \
                                                         (T*)p->y, p->Do, p->Ho, p->Wo, p->Nout, p->act, p->act_param)

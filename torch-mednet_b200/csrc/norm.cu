@@ -380,14 +380,15 @@ __global__ void upcat_gn_finalize_kernel(const float* __restrict__ pa, const flo
 template <typename T, int V>
 __global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ y,
                                       const float* __restrict__ ab, int D, int H, int W, int Cs, int Cl, int ncol,
-                                      int rows_per_slab) {
+                                      int lines_per_slab) {
+  // a "line" is one (z, y) row of W voxels; thread (tx, ty) owns channel vector tx and voxels x = ty, ty + R, ...
   const int col = blockIdx.z * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const int n = blockIdx.y, slab = blockIdx.x;
-  const int S = D * H * W, C = Cs + Cl, ncs = Cs / V;
+  const int C = Cs + Cl, ncs = Cs / V, nlines = D * H;
   const int h = H >> 1, w = W >> 1;
-  const int r0 = slab * rows_per_slab;
-  const int r1 = min(r0 + rows_per_slab, S);
+  const int l0 = slab * lines_per_slab;
+  const int l1 = min(l0 + lines_per_slab, nlines);
   float a[V], b[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -395,21 +396,21 @@ __global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __res
     b[i] = ab[((int64_t)n * 2 + 1) * C + col * V + i];
   }
   const bool from_skip = col < ncs;
-  const T* sbase = skip + (int64_t)n * S * Cs + col * V;
-  const T* lbase = low + (int64_t)n * (S >> 3) * Cl + (col - ncs) * V;
-  T* ybase = y + (int64_t)n * S * C + col * V;
-  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float v[V];
-    if (from_skip) {
-      load_vec<T, V>(sbase + (int64_t)r * Cs, v);
-    } else {
-      const int x = r % W, t = r / W, yy = t % H, z = t / H;
-      const int rl = ((z >> 1) * h + (yy >> 1)) * w + (x >> 1);
-      load_vec<T, V>(lbase + (int64_t)rl * Cl, v);
-    }
+  const T* sbase = skip + (int64_t)n * nlines * W * Cs + col * V;
+  const T* lbase = low + (int64_t)n * (nlines >> 2) * w * Cl + (col - ncs) * V;
+  T* ybase = y + (int64_t)n * nlines * W * C + col * V;
+  for (int l = l0; l < l1; ++l) {
+    const int z = l / H, yy = l - z * H;
+    const int64_t r0 = (int64_t)l * W;
+    const int64_t rl0 = (int64_t)((z >> 1) * h + (yy >> 1)) * w;
+    for (int x = threadIdx.y; x < W; x += blockDim.y) {
+      float v[V];
+      if (from_skip) load_vec<T, V>(sbase + (r0 + x) * Cs, v);
+      else load_vec<T, V>(lbase + (rl0 + (x >> 1)) * Cl, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = fmaf(v[i], a[i], b[i]);
-    store_vec<T, V>(ybase + (int64_t)r * C, v);
+      for (int i = 0; i < V; ++i) v[i] = fmaf(v[i], a[i], b[i]);
+      store_vec<T, V>(ybase + (r0 + x) * C, v);
+    }
   }
 }
 
@@ -417,36 +418,37 @@ __global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __res
 template <typename T, int V>
 __global__ void upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T* __restrict__ low,
                                             const T* __restrict__ dy, float* __restrict__ partial, int D, int H, int W,
-                                            int Cs, int Cl, int ncol, int rows_per_slab, int nslab) {
+                                            int Cs, int Cl, int ncol, int lines_per_slab, int nslab) {
   extern __shared__ float sm[];
   const int col = blockIdx.z * blockDim.x + threadIdx.x;
   const int n = blockIdx.y, slab = blockIdx.x;
-  const int S = D * H * W, C = Cs + Cl, ncs = Cs / V;
+  const int C = Cs + Cl, ncs = Cs / V, nlines = D * H;
   const int h = H >> 1, w = W >> 1;
-  const int r0 = slab * rows_per_slab;
-  const int r1 = min(r0 + rows_per_slab, S);
+  const int l0 = slab * lines_per_slab;
+  const int l1 = min(l0 + lines_per_slab, nlines);
   float acc[2 * V];
 #pragma unroll
   for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
   const bool active = col < ncol;
   if (active) {
     const bool from_skip = col < ncs;
-    const T* sbase = skip + (int64_t)n * S * Cs + col * V;
-    const T* lbase = low + (int64_t)n * (S >> 3) * Cl + (col - ncs) * V;
-    const T* gbase = dy + (int64_t)n * S * C + col * V;
-    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      float xv[V], gv[V];
-      if (from_skip) {
-        load_vec<T, V>(sbase + (int64_t)r * Cs, xv);
-      } else {
-        const int x = r % W, t = r / W, yy = t % H, z = t / H;
-        load_vec<T, V>(lbase + (int64_t)(((z >> 1) * h + (yy >> 1)) * w + (x >> 1)) * Cl, xv);
-      }
-      load_vec<T, V>(gbase + (int64_t)r * C, gv);
+    const T* sbase = skip + (int64_t)n * nlines * W * Cs + col * V;
+    const T* lbase = low + (int64_t)n * (nlines >> 2) * w * Cl + (col - ncs) * V;
+    const T* gbase = dy + (int64_t)n * nlines * W * C + col * V;
+    for (int l = l0; l < l1; ++l) {
+      const int z = l / H, yy = l - z * H;
+      const int64_t r0 = (int64_t)l * W;
+      const int64_t rl0 = (int64_t)((z >> 1) * h + (yy >> 1)) * w;
+      for (int x = threadIdx.y; x < W; x += blockDim.y) {
+        float xv[V], gv[V];
+        if (from_skip) load_vec<T, V>(sbase + (r0 + x) * Cs, xv);
+        else load_vec<T, V>(lbase + (rl0 + (x >> 1)) * Cl, xv);
+        load_vec<T, V>(gbase + (r0 + x) * C, gv);
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        acc[i] += gv[i];
-        acc[V + i] += gv[i] * xv[i];
+        for (int i = 0; i < V; ++i) {
+          acc[i] += gv[i];
+          acc[V + i] += gv[i] * xv[i];
+        }
       }
     }
   }
@@ -656,7 +658,7 @@ UpcatPlan upcat_plan(int N, int D, int H, int W, int Cs, int Cl, int dtype) {
   const int64_t S = (int64_t)D * H * W;
   u.pa = make_plan(N, S, Cs, eb);
   u.pb = make_plan(N, S / 8, Cl, eb);
-  u.pc = make_plan(N, S, Cs + Cl, eb, u.V);
+  u.pc = make_plan(N, (int64_t)D * H, Cs + Cl, eb, u.V);   // slabs of (z, y) LINES of W voxels (concat-grid kernels)
   u.pa_bytes = align_up((size_t)N * u.pa.nslab * 2 * Cs * sizeof(float), 256);
   u.pb_bytes = align_up((size_t)N * u.pb.nslab * 2 * Cl * sizeof(float), 256);
   return u;
