@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -199,6 +200,8 @@ def main():
     rank, local, world = init_distributed()
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
+    from mednet_b200._abi import check, lib
+    check(lib().mednet_tcgen05_set_option(b"dual_issue", args.dual_issue), "tcgen05_set_option")
     hp = hparams_for(wl)
     cls = LandmarkUNet3D if wl["heatmaps"] else SegmentationUNet3D
     model = cls(hp, conv_impl=args.conv_impl).to(dev)

@@ -422,6 +422,9 @@ int mednet_tile_scatter(const mednet_tile_scatter_params* p, mednet_stream_t str
  *   base_offset_mode: 0 -> descriptor base_offset 0; 1 -> (start >> 7) & 7; 2 -> (start / row_bytes) & 7.
  * ---------------------------------------------------------------------------------------------- */
 int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_halo, int base_offset_mode);
+/* Tuning switches of the tensor-core conv (A/B measurements): "dual_issue" 0|1 = second MMA-issuing thread for
+ * output tiles of <= 96 channels (default 1). */
+int mednet_tcgen05_set_option(const char* name, int value);
 int mednet_tcgen05_probe(const void* a_bf16 /* [rows][row_bytes/2] */, int32_t row_bytes, int32_t rows,
                          int32_t row_shift, int32_t sbo_bytes, int32_t base_offset_mode,
                          float* out /* [128][row_bytes/2] */, mednet_stream_t stream);

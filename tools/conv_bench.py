@@ -39,10 +39,15 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--passes", default="fprop,wgrad")
     ap.add_argument("--wgrad-impl", default="auto")
+    ap.add_argument("--dual-issue", type=int, default=1)
+    ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
     ops.calibrate_tcgen05()
-    for cin, cout, div in LAYERS:
+    from mednet_b200._abi import check, lib
+    check(lib().mednet_tcgen05_set_option(b"dual_issue", a.dual_issue), "set_option")
+    layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
+    for cin, cout, div in layers:
         s = a.edge // div
         x = torch.randn(a.batch, s, s, s, cin, device=dev).to(torch.bfloat16)
         dy = torch.randn(a.batch, s, s, s, cout, device=dev).to(torch.bfloat16)
@@ -52,7 +57,14 @@ def main():
             impl = ops.conv_select_impl(x.shape, (s, s, s), cin, cout, x.dtype, 0, "auto", x.data_ptr())
             wp = ops.k_pack_weights(w, cin, cout, x.dtype, 2 if impl == 2 else 0)
             ms = timed(lambda: ops.k_conv3(x, wp, cout, (s, s, s), 0, impl), a.reps)
-            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="fprop", impl=impl, ms=ms, tflops=flops / ms / 1e9)))
+            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="fprop", impl=impl, ms=ms, tflops=flops / ms / 1e9,
+                                  dual_issue=a.dual_issue)))
+        if "dgrad" in a.passes:
+            impl = ops.conv_select_impl(dy.shape, (s, s, s), cout, cin, dy.dtype, 0, "auto", dy.data_ptr())
+            wp = ops.k_pack_weights(w, cin, cout, dy.dtype, 3 if impl == 2 else 1)
+            ms = timed(lambda: ops.k_conv3(dy, wp, cin, (s, s, s), 0, impl), a.reps)
+            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="dgrad", impl=impl, ms=ms, tflops=flops / ms / 1e9,
+                                  dual_issue=a.dual_issue)))
         if "wgrad" in a.passes:
             ms = timed(lambda: ops.k_wgrad(dy, x, 0, a.wgrad_impl), a.reps)
             print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9)))

@@ -18,15 +18,22 @@ if [[ " $WHAT " == *" bench "* ]]; then
   python bench.py --steps 8 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
   python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
 fi
-if [[ " $WHAT " == *" ncu "* ]]; then
-  CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+[[ " $WHAT " == *" ncu "* ]] && WHAT="$WHAT launches kmetrics full"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+if [[ " $WHAT " == *" launches "* || " $WHAT " == *" kmetrics "* || " $WHAT " == *" full "* ]]; then
   $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
+fi
+if [[ " $WHAT " == *" launches "* ]]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_a_$TAG.log 2>&1
   echo "ncu launches rc=$?"
-  M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,launch__registers_per_thread,launch__grid_size,smsp__cycles_active.avg
-  # one training step's worth of every kernel of ours (first step: same shapes as the timed ones), metrics only
-  ncu --clock-control none --metrics $M -k regex:'mednet' -c 330 --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
+fi
+if [[ " $WHAT " == *" kmetrics "* ]]; then
+  M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,launch__registers_per_thread,launch__grid_size
+  # one training step's worth of every kernel of ours (-k matches the unqualified function name), metrics only
+  ncu --clock-control none --metrics $M -k regex:'_kernel' -c 420 --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
   echo "ncu per-kernel metrics rc=$?"
+fi
+if [[ " $WHAT " == *" full "* ]]; then
   # the dominant kernel with the full set + source (2 launches of the widest layer: skip the first 20 conv launches)
   ncu --set full --clock-control none --import-source on -k regex:conv3_tc_kernel -s 20 -c 2 -f -o $OUT/conv3_tc_$TAG $CMD > $OUT/ncu_b_$TAG.log 2>&1
   echo "ncu conv full rc=$?"

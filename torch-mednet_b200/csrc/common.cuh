@@ -59,6 +59,19 @@ __device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&out)[V
   for (int i = 0; i < V; ++i) out[i] = to_f32<T>(u.t[i]);
 }
 
+// split form: issue the raw load now, convert later (keeps only sizeof(T)*V bytes of registers live per pending load)
+template <typename T, int V>
+__device__ __forceinline__ typename RawVec<sizeof(T) * V>::type load_raw(const T* __restrict__ p) {
+  return *reinterpret_cast<const typename RawVec<sizeof(T) * V>::type*>(p);
+}
+template <typename T, int V>
+__device__ __forceinline__ void cvt_raw(const typename RawVec<sizeof(T) * V>::type& r, float (&out)[V]) {
+  union { typename RawVec<sizeof(T) * V>::type r; T t[V]; } u;
+  u.r = r;
+#pragma unroll
+  for (int i = 0; i < V; ++i) out[i] = to_f32<T>(u.t[i]);
+}
+
 template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&in)[V]) {
   typedef typename RawVec<sizeof(T) * V>::type R;

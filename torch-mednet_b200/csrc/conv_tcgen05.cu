@@ -15,6 +15,8 @@
 // Warp roles: 0 = halo TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+ TMEM alloc), 3..6 =
 // epilogue (one TMEM lane quadrant each).  All hand-offs are mbarriers; halo planes are released as soon
 // as their last kd phase has been issued so the next chunk's planes stream in under the current MMAs.
+#include <string.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -44,11 +46,12 @@ static int g_enabled[3] = {0, 0, 0};
 static int g_dense_halo[3] = {0, 0, 0};        // 0: halo rows padded to a 16-voxel pitch, one TMA per (d,h) row
                                                // 1: dense 10-voxel pitch, one TMA box per halo plane
 static int g_base_offset_mode[3] = {1, 1, 1};  // 0: base_offset = 0; 1: (addr >> 7) & 7; 2: (addr / row_bytes) & 7
+static int g_dual_issue = 1;                  // mednet_tcgen05_set_option("dual_issue", 0|1)
 static inline int rb_class(int rb) { return rb == 128 ? 0 : rb == 64 ? 1 : 2; }
 
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
 constexpr int MAX_PLANES = 6, MAX_BSTAGES = 8;
-constexpr int NUM_THREADS = 224;
+constexpr int NUM_THREADS = 256;     // warps: 0 halo TMA, 1 weight TMA, 2 MMA issuer (+TMEM alloc), 3..6 epilogue, 7 second MMA issuer
 
 struct TcConv {
   int N, D, H, W, K, Nout;
@@ -56,6 +59,7 @@ struct TcConv {
   int64_t num_tiles;
   int TD, Ntile, nchunks, RB, pitch, per_row, bo_mode;
   int plane_bytes, b_bytes, BS, acc_stages, tmem_cols;
+  int dual;                    // 1: two MMA-issuing threads, each owning half of the brick's d-planes
   int act;
   float act_param;
   const float* bias;
@@ -74,6 +78,76 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConv& p, int64_t t) {
   c.d0 = (int)(t % p.tiles_d) * p.TD;
   c.n = (int)(t / p.tiles_d);
   return c;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply_t(float x, float a) {
+  if (ACT == MEDNET_ACT_RELU) return x > 0.f ? x : 0.f;
+  if (ACT == MEDNET_ACT_LEAKY) return x > 0.f ? x : a * x;
+  if (ACT == MEDNET_ACT_ELU) return x > 0.f ? x : expm1f(x);
+  return x;
+}
+
+// Epilogue of one CTA (warps 3..6, one TMEM lane quadrant each): TMEM -> registers -> (+bias, +addend, activation) -> bf16
+// NDHWC rows.  Accumulator row m = voxel (h, w) of the brick plane.
+template <int ACT>
+__device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                              int warp, int lane) {
+  const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int m = q * 32 + lane;
+  const int hh = m >> 3, ww = m & 7;
+  uint32_t tcount = 0;
+  for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+    const TileCoord tc_ = decode_tile(p, t);
+    const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
+    tc::mbar_wait(&acc_full[as], aph);
+    tc::tc_fence_after();
+    const int h = tc_.h0 + hh, w = tc_.w0 + ww;
+    for (int dz = 0; dz < p.TD; ++dz) {
+      const int d = tc_.d0 + dz;
+      const bool inb = d < p.D && h < p.H && w < p.W;
+      const int64_t vox = (((int64_t)tc_.n * p.D + d) * p.H + h) * p.W + w;
+      bf16* yrow = p.y + vox * p.Nout + tc_.n0;
+      const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
+      for (int j = 0; j < p.Ntile; j += 16) {
+        uint32_t r[16];
+        tc::tmem_ld_x16(taddr + (uint32_t)j, r);
+        tc::tmem_ld_wait();
+        if (inb) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
+            const float4* bq = reinterpret_cast<const float4*>(p.bias + tc_.n0 + j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bq + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          }
+          if (arow != nullptr) {
+            float a0[8], a1[8];
+            load_vec<bf16, 8>(arow + j, a0);
+            load_vec<bf16, 8>(arow + j + 8, a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] += a0[i]; v[8 + i] += a1[i]; }
+          }
+          float o0[8], o1[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o0[i] = act_apply_t<ACT>(v[i], p.act_param);
+            o1[i] = act_apply_t<ACT>(v[8 + i], p.act_param);
+          }
+          store_vec<bf16, 8>(yrow + j, o0);
+          store_vec<bf16, 8>(yrow + j + 8, o1);
+        }
+      }
+    }
+    tc::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -95,9 +169,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int nplanes = p.TD + 2;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nplanes; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.BS; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    const uint32_t nissue = p.dual ? 2u : 1u;         // every issuer commits to the barriers the MMAs release
+    for (int i = 0; i < nplanes; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], nissue); }
+    for (int i = 0; i < p.BS; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], nissue); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], nissue); tc::mbar_init(&acc_empty[i], 4); }
     tc::fence_barrier_init();
     tc::tma_prefetch_desc(&map_x);
     tc::tma_prefetch_desc(&map_w);
@@ -150,20 +225,27 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 2 || warp == 7) {
+    // ===================== MMA issuer(s) =====================
+    // A single issuing thread sustains one M=128 MMA per ~55 clk whatever N is (measured, csrc/umma_lab.cu), while the
+    // tensor pipe needs only N/2 clk and shared memory (4 KB + 32 N B)/128 clk per MMA.  For N <= 96 a second issuer
+    // (warp 7) takes half of the brick's d-planes (its own accumulators), which moves the bound from the issue rate to
+    // the shared-memory read rate (48 clk at N = 64).
     // The issuing thread is a serial instruction stream: every instruction between two tcgen05.mma costs
     // ~4-5 clk of dependent latency, and an M=128 MMA only occupies the tensor pipe for N/2 clk (32 clk at
     // N=64).  So the descriptors are built ONCE; per MMA only the 32-bit address word is advanced by
     // register-resident offsets (measured: 111 clk/MMA with per-MMA descriptor construction, 55 clk lean).
-    if (tc::elect_one()) {
+    const int issuer = warp == 2 ? 0 : 1;
+    const int TDI = p.dual ? p.TD / 2 : p.TD;           // planes per issuer (kernel-uniform loop bound)
+    if ((issuer == 0 || p.dual) && tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.Ntile, 0, 0);
       const uint32_t layout = p.RB == 128 ? tc::SWZ_128B : (p.RB == 64 ? tc::SWZ_64B : tc::SWZ_32B);
       const uint64_t da_base = tc::make_smem_desc(tc::smem_u32(a_base), 16, (uint32_t)(p.pitch * p.RB), 0, layout);
       const uint64_t db_base = tc::make_smem_desc(tc::smem_u32(b_base), 16, (uint32_t)(8 * p.RB), 0, layout);
       const uint32_t a_hi = (uint32_t)(da_base >> 32), b_hi = (uint32_t)(db_base >> 32);
-      const uint32_t a_lo0 = (uint32_t)da_base, b_lo0 = (uint32_t)db_base;
       const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4, b16 = (uint32_t)p.b_bytes >> 4;
+      const uint32_t a_lo0 = (uint32_t)da_base + (uint32_t)(issuer * TDI) * plane16, b_lo0 = (uint32_t)db_base;
+      const uint32_t d_issuer = (uint32_t)(issuer * TDI * p.Ntile);
       uint32_t tapoff[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) tapoff[i] = (uint32_t)(((i / 3) * p.pitch + (i % 3)) * p.RB) >> 4;
@@ -174,7 +256,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
         tc::mbar_wait(&acc_empty[as], aph ^ 1u);
         tc::tc_fence_after();
-        const uint32_t d_tile = tmem_base + as * (uint32_t)(p.TD * p.Ntile);
+        const uint32_t d_tile = tmem_base + as * (uint32_t)(p.TD * p.Ntile) + d_issuer;
         for (int c = 0; c < p.nchunks; ++c, ++ait) {
           for (int kd = 0; kd < 3; ++kd) {
             if (kd == 0) {
@@ -192,7 +274,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               uint32_t a_lo = a_kd + tapoff[khw];
               uint32_t d_tmem = d_tile;
               const uint32_t first = (uint32_t)(c | kd | khw);
-              for (int dz = 0; dz < p.TD; ++dz) {
+              for (int dz = 0; dz < TDI; ++dz) {
                 if (ksteps == 4) {
                   tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
                   tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
@@ -224,56 +306,14 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;            // accumulator row = voxel (h, w) of the brick plane
-    const int hh = m >> 3, ww = m & 7;
-    uint32_t tcount = 0;
-    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
-      const TileCoord tc_ = decode_tile(p, t);
-      const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-      tc::mbar_wait(&acc_full[as], aph);
-      tc::tc_fence_after();
-      const int h = tc_.h0 + hh, w = tc_.w0 + ww;
-      for (int dz = 0; dz < p.TD; ++dz) {
-        const int d = tc_.d0 + dz;
-        const bool inb = d < p.D && h < p.H && w < p.W;
-        const int64_t vox = (((int64_t)tc_.n * p.D + d) * p.H + h) * p.W + w;
-        bf16* yrow = p.y + vox * p.Nout + tc_.n0;
-        const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
-        for (int j = 0; j < p.Ntile; j += 16) {
-          uint32_t r[16];
-          tc::tmem_ld_x16(taddr + (uint32_t)j, r);
-          tc::tmem_ld_wait();
-          if (inb) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + tc_.n0 + j + i);
-            }
-            if (arow != nullptr) {
-              float a0[8], a1[8];
-              load_vec<bf16, 8>(arow + j, a0);
-              load_vec<bf16, 8>(arow + j + 8, a1);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { v[i] += a0[i]; v[8 + i] += a1[i]; }
-            }
-            float o0[8], o1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              o0[i] = act_apply(v[i], p.act, p.act_param);
-              o1[i] = act_apply(v[8 + i], p.act, p.act_param);
-            }
-            store_vec<bf16, 8>(yrow + j, o0);
-            store_vec<bf16, 8>(yrow + j + 8, o1);
-          }
-        }
-      }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+    // the activation is a template parameter: a run-time switch inside the per-element code is compiled to either
+    // selects or an indirect branch per element depending on unrelated details of the kernel (measured: 2x slower
+    // epilogue-bound layers), so it is dispatched once per CTA here
+    switch (p.act) {
+      case MEDNET_ACT_RELU: epilogue_loop<MEDNET_ACT_RELU>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case MEDNET_ACT_LEAKY: epilogue_loop<MEDNET_ACT_LEAKY>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case MEDNET_ACT_ELU: epilogue_loop<MEDNET_ACT_ELU>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
+      default: epilogue_loop<MEDNET_ACT_NONE>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
     }
   }
   tc::tc_fence_before();
@@ -312,6 +352,7 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   if (bs < 2) return false;
   p.BS = bs;
   p.acc_stages = (2 * p.TD * p.Ntile <= 512) ? 2 : 1;
+  p.dual = (g_dual_issue && p.Ntile <= 96 && p.TD >= 2 && (p.TD % 2) == 0) ? 1 : 0;
   int cols = p.acc_stages * p.TD * p.Ntile, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
@@ -330,7 +371,7 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
 bool tc_fprop_supported(const mednet_conv3d_params* q) {
   if (q->dtype != MEDNET_BF16 || q->gather != MEDNET_GATHER_CONV3) return false;
   if (!mednet_device_has_tcgen05()) return false;
-  if (((uintptr_t)q->x | (uintptr_t)q->w | (uintptr_t)q->y | (uintptr_t)q->addend) & 15) return false;
+  if (((uintptr_t)q->x | (uintptr_t)q->w | (uintptr_t)q->y | (uintptr_t)q->addend | (uintptr_t)q->bias) & 15) return false;
   TcConv p;
   return plan_tc(q, &p);
 }
@@ -462,6 +503,12 @@ extern "C" int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_ha
   g_dense_halo[rc] = dense_halo ? 1 : 0;
   g_base_offset_mode[rc] = base_offset_mode;
   return MEDNET_OK;
+}
+
+extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
+  MEDNET_REQUIRE(name != nullptr, MEDNET_EINVAL);
+  if (strcmp(name, "dual_issue") == 0) { g_dual_issue = value ? 1 : 0; return MEDNET_OK; }
+  return MEDNET_EINVAL;
 }
 
 extern "C" int mednet_tcgen05_probe(const void* a_bf16, int32_t row_bytes, int32_t rows, int32_t row_shift,

@@ -6,6 +6,10 @@
 
 namespace mednet {
 
+constexpr int UNR = 4;    // rows in flight per thread in the concat-grid kernels (few, fat blocks: memory-level parallelism)
+constexpr int UAPP = 1;   // plain GroupNorm apply: one row per iteration
+constexpr int USTD = 2;   // plain GroupNorm kernels: 1 row per stream (USTD / 2) -- occupancy already hides the latency
+
 // ------------------------------------------------------------------------------------------------
 // launch plan shared by stats / apply / backward kernels: block = (ncol_t, R) threads, thread (tx,ty)
 // owns channel vector `tx` and walks rows ty, ty+R, ... of its slab -> a block reads R consecutive
@@ -16,7 +20,7 @@ struct SlabPlan {
   int64_t rows_per_slab;
 };
 
-static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force_v = 0) {
+static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force_v = 0, int slabs_per_sm = 6) {
   SlabPlan p;
   p.V = force_v > 0 ? force_v : pick_vec(C, elem_bytes);
   p.ncol = C / p.V;
@@ -30,7 +34,7 @@ static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force
     p.coltiles = ceil_div(p.ncol, 256);
     p.R = 1;
   }
-  int64_t target = (int64_t)sm_count_cached() * 6;
+  int64_t target = (int64_t)sm_count_cached() * slabs_per_sm;
   int64_t nslab = target / (N * p.coltiles);
   int64_t max_slab = S / ((int64_t)p.R * 4);
   if (nslab > max_slab) nslab = max_slab;
@@ -71,14 +75,23 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
   const bool active = col < ncol;
   if (active) {
     const T* base = x + (int64_t)n * S * C + (int64_t)col * V;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      float v[V];
-      load_vec<T, V>(base + r * C, v);
+    const int64_t R = blockDim.y;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += USTD * R) {      // USTD independent 16-byte loads in flight per thread
+      typename RawVec<sizeof(T) * V>::type raw[USTD];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        acc[i] += v[i];
-        acc[V + i] += v[i] * v[i];
-      }
+      for (int u = 0; u < USTD; ++u)
+        if (r + u * R < r1) raw[u] = load_raw<T, V>(base + (r + u * R) * C);
+#pragma unroll
+      for (int u = 0; u < USTD; ++u)
+        if (r + u * R < r1) {
+          float v[V];
+          cvt_raw<T, V>(raw[u], v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            acc[i] += v[i];
+            acc[V + i] += v[i] * v[i];
+          }
+        }
     }
   }
   float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
@@ -141,19 +154,31 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ r
     b[i] = ab[((int64_t)n * 2 + 1) * C + col * V + i];
   }
   const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
-  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float v[V];
-    load_vec<T, V>(x + base + r * C, v);
-    if (residual != nullptr) {
-      float rr[V];
-      load_vec<T, V>(residual + base + r * C, rr);
+  const int64_t R = blockDim.y;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += UAPP * R) {
+    typename RawVec<sizeof(T) * V>::type rx[UAPP], rres[UAPP];
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]) + rr[i], act, act_param);
-    } else {
+    for (int u = 0; u < UAPP; ++u)
+      if (r + u * R < r1) {
+        rx[u] = load_raw<T, V>(x + base + (r + u * R) * C);
+        if (residual != nullptr) rres[u] = load_raw<T, V>(residual + base + (r + u * R) * C);
+      }
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]), act, act_param);
-    }
-    store_vec<T, V>(y + base + r * C, v);
+    for (int u = 0; u < UAPP; ++u)
+      if (r + u * R < r1) {
+        float v[V];
+        cvt_raw<T, V>(rx[u], v);
+        if (residual != nullptr) {
+          float rr[V];
+          cvt_raw<T, V>(rres[u], rr);
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]) + rr[i], act, act_param);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i], a[i], b[i]), act, act_param);
+        }
+        store_vec<T, V>(y + base + (r + u * R) * C, v);
+      }
   }
 }
 
@@ -174,21 +199,35 @@ __global__ void gn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
   const bool active = col < ncol;
   if (active) {
     const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      float xv[V], gv[V];
-      load_vec<T, V>(x + base + r * C, xv);
-      load_vec<T, V>(dy + base + r * C, gv);
-      if (act != MEDNET_ACT_NONE) {
-        float yv[V];
-        load_vec<T, V>(y + base + r * C, yv);
+    const int64_t R = blockDim.y;
+    constexpr int U2 = USTD / 2;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += U2 * R) {
+      typename RawVec<sizeof(T) * V>::type rx[U2], rg[U2], ry[U2];
 #pragma unroll
-        for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
-      }
+      for (int u = 0; u < U2; ++u)
+        if (r + u * R < r1) {
+          rx[u] = load_raw<T, V>(x + base + (r + u * R) * C);
+          rg[u] = load_raw<T, V>(dy + base + (r + u * R) * C);
+          if (act != MEDNET_ACT_NONE) ry[u] = load_raw<T, V>(y + base + (r + u * R) * C);
+        }
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        acc[i] += gv[i];
-        acc[V + i] += gv[i] * xv[i];
-      }
+      for (int u = 0; u < U2; ++u)
+        if (r + u * R < r1) {
+          float xv[V], gv[V];
+          cvt_raw<T, V>(rx[u], xv);
+          cvt_raw<T, V>(rg[u], gv);
+          if (act != MEDNET_ACT_NONE) {
+            float yv[V];
+            cvt_raw<T, V>(ry[u], yv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            acc[i] += gv[i];
+            acc[V + i] += gv[i] * xv[i];
+          }
+        }
     }
   }
   float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
@@ -279,26 +318,40 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     Cc[i] = coef[((int64_t)n * 3 + 2) * C + col * V + i];
   }
   const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
-  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float xv[V], gv[V];
-    load_vec<T, V>(x + base + r * C, xv);
-    load_vec<T, V>(dy + base + r * C, gv);
-    if (act != MEDNET_ACT_NONE) {
-      float yv[V];
-      load_vec<T, V>(y + base + r * C, yv);
+  const int64_t R = blockDim.y;
+  constexpr int U2 = USTD / 2;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += U2 * R) {
+    typename RawVec<sizeof(T) * V>::type rx[U2], rg[U2], ry[U2];
 #pragma unroll
-      for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
-    }
-    if (dresidual != nullptr) store_vec<T, V>(dresidual + base + r * C, gv);
-    if (in_act != MEDNET_ACT_NONE) {            // deferred derivative of the activation that produced x
+    for (int u = 0; u < U2; ++u)
+      if (r + u * R < r1) {
+        rx[u] = load_raw<T, V>(x + base + (r + u * R) * C);
+        rg[u] = load_raw<T, V>(dy + base + (r + u * R) * C);
+        if (act != MEDNET_ACT_NONE) ry[u] = load_raw<T, V>(y + base + (r + u * R) * C);
+      }
 #pragma unroll
-      for (int i = 0; i < V; ++i)
-        xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], in_act, in_act_param);
-    } else {
+    for (int u = 0; u < U2; ++u)
+      if (r + u * R < r1) {
+        float xv[V], gv[V];
+        cvt_raw<T, V>(rx[u], xv);
+        cvt_raw<T, V>(rg[u], gv);
+        if (act != MEDNET_ACT_NONE) {
+          float yv[V];
+          cvt_raw<T, V>(ry[u], yv);
 #pragma unroll
-      for (int i = 0; i < V; ++i) xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i]));
-    }
-    store_vec<T, V>(dx + base + r * C, xv);
+          for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
+        }
+        if (dresidual != nullptr) store_vec<T, V>(dresidual + base + (r + u * R) * C, gv);
+        if (in_act != MEDNET_ACT_NONE) {            // deferred derivative of the activation that produced x
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], in_act, in_act_param);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i]));
+        }
+        store_vec<T, V>(dx + base + (r + u * R) * C, xv);
+      }
   }
 }
 
@@ -378,7 +431,7 @@ __global__ void upcat_gn_finalize_kernel(const float* __restrict__ pa, const flo
 }
 
 template <typename T, int V>
-__global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ y,
+__global__ void __launch_bounds__(256, 4) upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __restrict__ low, T* __restrict__ y,
                                       const float* __restrict__ ab, int D, int H, int W, int Cs, int Cl, int ncol,
                                       int lines_per_slab) {
   // a "line" is one (z, y) row of W voxels; thread (tx, ty) owns channel vector tx and voxels x = ty, ty + R, ...
@@ -403,20 +456,32 @@ __global__ void upcat_gn_apply_kernel(const T* __restrict__ skip, const T* __res
     const int z = l / H, yy = l - z * H;
     const int64_t r0 = (int64_t)l * W;
     const int64_t rl0 = (int64_t)((z >> 1) * h + (yy >> 1)) * w;
-    for (int x = threadIdx.y; x < W; x += blockDim.y) {
-      float v[V];
-      if (from_skip) load_vec<T, V>(sbase + (r0 + x) * Cs, v);
-      else load_vec<T, V>(lbase + (rl0 + (x >> 1)) * Cl, v);
+    const int R = blockDim.y;
+    for (int x0 = threadIdx.y; x0 < W; x0 += UNR * R) {
+      typename RawVec<sizeof(T) * V>::type raw[UNR];
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = fmaf(v[i], a[i], b[i]);
-      store_vec<T, V>(ybase + (r0 + x) * C, v);
+      for (int u = 0; u < UNR; ++u) {
+        const int x = x0 + u * R;
+        if (x < W) raw[u] = from_skip ? load_raw<T, V>(sbase + (r0 + x) * Cs) : load_raw<T, V>(lbase + (rl0 + (x >> 1)) * Cl);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int x = x0 + u * R;
+        if (x < W) {
+          float v[V];
+          cvt_raw<T, V>(raw[u], v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[i] = fmaf(v[i], a[i], b[i]);
+          store_vec<T, V>(ybase + (r0 + x) * C, v);
+        }
+      }
     }
   }
 }
 
 // backward stage 1 on the virtual concat: partial[n][slab][{sum dy, sum dy*x}][C]
 template <typename T, int V>
-__global__ void upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T* __restrict__ low,
+__global__ void __launch_bounds__(256, 4) upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T* __restrict__ low,
                                             const T* __restrict__ dy, float* __restrict__ partial, int D, int H, int W,
                                             int Cs, int Cl, int ncol, int lines_per_slab, int nslab) {
   extern __shared__ float sm[];
@@ -439,15 +504,29 @@ __global__ void upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T*
       const int z = l / H, yy = l - z * H;
       const int64_t r0 = (int64_t)l * W;
       const int64_t rl0 = (int64_t)((z >> 1) * h + (yy >> 1)) * w;
-      for (int x = threadIdx.y; x < W; x += blockDim.y) {
-        float xv[V], gv[V];
-        if (from_skip) load_vec<T, V>(sbase + (r0 + x) * Cs, xv);
-        else load_vec<T, V>(lbase + (rl0 + (x >> 1)) * Cl, xv);
-        load_vec<T, V>(gbase + (r0 + x) * C, gv);
+      const int R = blockDim.y;
+      for (int x0 = threadIdx.y; x0 < W; x0 += UNR * R) {
+        typename RawVec<sizeof(T) * V>::type rx[UNR], rg[UNR];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          acc[i] += gv[i];
-          acc[V + i] += gv[i] * xv[i];
+        for (int u = 0; u < UNR; ++u) {
+          const int x = x0 + u * R;
+          if (x < W) {
+            rx[u] = from_skip ? load_raw<T, V>(sbase + (r0 + x) * Cs) : load_raw<T, V>(lbase + (rl0 + (x >> 1)) * Cl);
+            rg[u] = load_raw<T, V>(gbase + (r0 + x) * C);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (x0 + u * R < W) {
+            float xv[V], gv[V];
+            cvt_raw<T, V>(rx[u], xv);
+            cvt_raw<T, V>(rg[u], gv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              acc[i] += gv[i];
+              acc[V + i] += gv[i] * xv[i];
+            }
+          }
         }
       }
     }
@@ -460,7 +539,7 @@ __global__ void upcat_gn_bwd_partial_kernel(const T* __restrict__ skip, const T*
 
 // backward stage 3a: dskip = (A*dy + B*skip + Cc) * skip_act'(skip) for the first Cs concat channels
 template <typename T, int V>
-__global__ void upcat_gn_bwd_skip_kernel(const T* __restrict__ skip, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) upcat_gn_bwd_skip_kernel(const T* __restrict__ skip, const T* __restrict__ dy,
                                          const float* __restrict__ coef, T* __restrict__ dskip, int64_t S, int Cs, int C,
                                          int ncol, int64_t rows_per_slab, int act, float act_param) {
   const int col = blockIdx.z * blockDim.x + threadIdx.x;
@@ -479,14 +558,26 @@ __global__ void upcat_gn_bwd_skip_kernel(const T* __restrict__ skip, const T* __
   const T* xb = skip + (int64_t)n * S * Cs + col * V;
   const T* gb = dy + (int64_t)n * S * C + col * V;
   T* ob = dskip + (int64_t)n * S * Cs + col * V;
-  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float xv[V], gv[V];
-    load_vec<T, V>(xb + r * Cs, xv);
-    load_vec<T, V>(gb + r * C, gv);
+  const int64_t R = blockDim.y;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += UNR * R) {
+    typename RawVec<sizeof(T) * V>::type rx[UNR], rg[UNR];
 #pragma unroll
-    for (int i = 0; i < V; ++i)
-      xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], act, act_param);
-    store_vec<T, V>(ob + r * Cs, xv);
+    for (int u = 0; u < UNR; ++u)
+      if (r + u * R < r1) {
+        rx[u] = load_raw<T, V>(xb + (r + u * R) * Cs);
+        rg[u] = load_raw<T, V>(gb + (r + u * R) * C);
+      }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (r + u * R < r1) {
+        float xv[V], gv[V];
+        cvt_raw<T, V>(rx[u], xv);
+        cvt_raw<T, V>(rg[u], gv);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          xv[i] = fmaf(A[i], gv[i], fmaf(B[i], xv[i], Cc[i])) * act_grad_from_out(xv[i], act, act_param);
+        store_vec<T, V>(ob + (r + u * R) * Cs, xv);
+      }
   }
 }
 
@@ -658,7 +749,7 @@ UpcatPlan upcat_plan(int N, int D, int H, int W, int Cs, int Cl, int dtype) {
   const int64_t S = (int64_t)D * H * W;
   u.pa = make_plan(N, S, Cs, eb);
   u.pb = make_plan(N, S / 8, Cl, eb);
-  u.pc = make_plan(N, (int64_t)D * H, Cs + Cl, eb, u.V);   // slabs of (z, y) LINES of W voxels (concat-grid kernels)
+  u.pc = make_plan(N, (int64_t)D * H, Cs + Cl, eb, u.V, 12);   // slabs of (z, y) LINES of W voxels (concat-grid kernels)
   u.pa_bytes = align_up((size_t)N * u.pa.nslab * 2 * Cs * sizeof(float), 256);
   u.pb_bytes = align_up((size_t)N * u.pb.nslab * 2 * Cl * sizeof(float), 256);
   return u;

@@ -11,7 +11,7 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmednet_b200.so")
+LIB_PATH = os.environ.get("MEDNET_B200_LIB", os.path.join(_PKG, "libmednet_b200.so"))   # override: A/B builds
 HEADER_PATH = os.environ.get(
     "MEDNET_B200_HEADER",
     os.path.join(os.path.dirname(os.path.dirname(_PKG)), "include", "mednet_b200.h"))
