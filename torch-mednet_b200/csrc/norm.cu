@@ -8,7 +8,7 @@ namespace mednet {
 
 constexpr int UNR = 4;    // rows in flight per thread in the concat-grid kernels (few, fat blocks: memory-level parallelism)
 constexpr int UAPP = 1;   // plain GroupNorm apply: one row per iteration
-constexpr int USTD = 2;   // plain GroupNorm kernels: 1 row per stream (USTD / 2) -- occupancy already hides the latency
+constexpr int USTD = 4;   // plain GroupNorm kernels: 4 rows in flight in the statistics pass, USTD / 2 per stream in the backward passes
 
 // ------------------------------------------------------------------------------------------------
 // launch plan shared by stats / apply / backward kernels: block = (ncol_t, R) threads, thread (tx,ty)
