@@ -40,12 +40,14 @@ def main():
     ap.add_argument("--passes", default="fprop,wgrad")
     ap.add_argument("--wgrad-impl", default="auto")
     ap.add_argument("--dual-issue", type=int, default=1)
+    ap.add_argument("--wt-fastest", type=int, default=1)
     ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
     ops.calibrate_tcgen05()
     from mednet_b200._abi import check, lib
     check(lib().mednet_tcgen05_set_option(b"dual_issue", a.dual_issue), "set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_wt_fastest", a.wt_fastest), "set_option")
     layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
     for cin, cout, div in layers:
         s = a.edge // div
@@ -67,7 +69,8 @@ def main():
                                   dual_issue=a.dual_issue)))
         if "wgrad" in a.passes:
             ms = timed(lambda: ops.k_wgrad(dy, x, 0, a.wgrad_impl), a.reps)
-            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9)))
+            print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9,
+                                  wt_fastest=a.wt_fastest)))
         del x, dy
 
 

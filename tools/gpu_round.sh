@@ -30,7 +30,7 @@ fi
 if [[ " $WHAT " == *" kmetrics "* ]]; then
   M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,launch__registers_per_thread,launch__grid_size
   # one training step's worth of every kernel of ours (-k matches the unqualified function name), metrics only
-  ncu --clock-control none --metrics $M -k regex:'_kernel' -c 420 --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
+  ncu --clock-control none --metrics $M -k regex:'^(conv|wgrad|gn_|upcat|maxpool|dice|adam|act_|pack_|cast_|transpose_|ce_|hm_)' -c 300 --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
   echo "ncu per-kernel metrics rc=$?"
 fi
 if [[ " $WHAT " == *" full "* ]]; then
