@@ -226,6 +226,8 @@ typedef struct {
   const void* dy; const uint8_t* idx; void* dx; int32_t N, D, H, W, C, dtype;
   const void* y;          /* pooled forward output (= x at the argmax); needed iff in_act != NONE       */
   int32_t in_act; float in_act_param;   /* deferred activation derivative of the producer of x         */
+  const void* addend;     /* optional [N, D, H, W, C]: gradient of x's OTHER consumer (the skip connection),
+                             added to dx in the same pass (replaces autograd's separate accumulation add)  */
 } mednet_pool_bwd_params;
 int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stream_t stream);
 /* Expand the 3-bit codes to ATen's int64 flat D*H*W indices, NCDHW order (parity checks only). */

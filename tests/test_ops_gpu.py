@@ -417,3 +417,30 @@ def test_groupnorm_over_virtual_concat(cs, cl, groups, small, acts, dtype):
     y2 = ops.GroupNormActFn.apply(ops.UpsampleConcatFn.apply(sg.detach(), lg.detach()), gg.detach(), bg.detach(), groups, 0, None)
     assert relerr(y.detach().float().cpu(), y2.float().cpu()) < (1e-6 if f32 else 8e-3)
     assert not ops.upcat_gn_supported(sg, lg[:, :1])             # non-2x geometry -> unfused path
+
+
+@pytest.mark.parametrize("c,shape", [(8, (6, 8, 10)), (12, (5, 7, 9)), (64, (4, 4, 4))])
+@pytest.mark.parametrize("act", [0, 1])
+def test_maxpool_with_fused_skip_gradient(c, shape, act):
+    """MaxPoolSkipFn returns (pooled, x) and adds the skip path's gradient inside the pool-backward kernel: same
+    gradient as autograd's pool backward + accumulate (components.py:210,224 + the encoder features of model.py:90-95)."""
+    torch.manual_seed(c)
+    pre = torch.randn(2, c, *shape, requires_grad=True)
+    x = _act_ref(pre, act)
+    out = F.max_pool3d(x, 2)
+    g1, g2 = torch.randn_like(out), torch.randn_like(x)
+    (out * g1).sum().backward(retain_graph=True)
+    gp = pre.grad.clone()
+    pre.grad = None
+    ((out * g1).sum() + (x * g2).sum()).backward()
+    xg = ndhwc(x.detach()).requires_grad_()
+    y, skip = ops.MaxPoolSkipFn.apply(xg, act)
+    assert torch.equal(ncdhw(y.detach()), out.detach()) and torch.equal(skip.detach(), xg.detach())
+    # the skip consumer applies the deferred mask itself (here: by hand), exactly like the join kernels do
+    mask = ndhwc((pre.detach() > 0).float() if act else torch.ones_like(pre))
+    ((y * ndhwc(g1)).sum() + (skip * (ndhwc(g2) * mask)).sum()).backward()
+    assert relerr(ncdhw(xg.grad), pre.grad) < 1e-6
+    xg2 = ndhwc(x.detach()).requires_grad_()
+    y2, _ = ops.MaxPoolSkipFn.apply(xg2, act)
+    (y2 * ndhwc(g1)).sum().backward()                       # skip branch unused -> plain pool backward
+    assert relerr(ncdhw(xg2.grad), gp) < 1e-6

@@ -60,26 +60,38 @@ __global__ void __launch_bounds__(256) conv1_fwd_vec_kernel(const T* __restrict_
 #pragma unroll
       for (int i = 0; i < V; ++i) wr[j][i] = j < nco ? w[(co0 + j) * Cin + col * V + i] : 0.f;
     for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
-      for (int ps = 0; ps < ncol; ++ps) {
-        const int vb = ps * vpp + vl;                            // voxel slot inside the block's 256
-        const int64_t r = base + vb;
-        float acc[CO_T];
+      for (int ps0 = 0; ps0 < ncol; ps0 += 8) {
+        // up to 8 passes' rows are loaded before any arithmetic (memory-level parallelism)
+        typename RawVec<sizeof(T) * V>::type raw[8];
 #pragma unroll
-        for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
-        if (r < total) {
-          float xv[V];
-          load_vec<T, V>(x + r * Cin + col * V, xv);
-#pragma unroll
-          for (int j = 0; j < CO_T; ++j)
-#pragma unroll
-            for (int i = 0; i < V; ++i) acc[j] = fmaf(xv[i], wr[j][i], acc[j]);
+        for (int u = 0; u < 8; ++u) {
+          const int64_t r = base + (ps0 + u) * vpp + vl;
+          if (ps0 + u < ncol && r < total) raw[u] = load_raw<T, V>(x + r * Cin + col * V);
         }
-        for (int off = 1; off < ncol; off <<= 1)
 #pragma unroll
-          for (int j = 0; j < CO_T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-        if (col == 0) {
+        for (int u = 0; u < 8; ++u) {
+          if (ps0 + u < ncol) {
+            const int vb = (ps0 + u) * vpp + vl;                 // voxel slot inside the block's 256
+            const int64_t r = base + vb;
+            float acc[CO_T];
 #pragma unroll
-          for (int j = 0; j < CO_T; ++j) tile[j][vb] = acc[j];
+            for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+            if (r < total) {
+              float xv[V];
+              cvt_raw<T, V>(raw[u], xv);
+#pragma unroll
+              for (int j = 0; j < CO_T; ++j)
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[j] = fmaf(xv[i], wr[j][i], acc[j]);
+            }
+            for (int off = 1; off < ncol; off <<= 1)
+#pragma unroll
+              for (int j = 0; j < CO_T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+            if (col == 0) {
+#pragma unroll
+              for (int j = 0; j < CO_T; ++j) tile[j][vb] = acc[j];
+            }
+          }
         }
       }
       __syncthreads();

@@ -96,7 +96,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
 template <typename T, int V>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
                                    int N, int D, int H, int W, int C, const T* __restrict__ y, int in_act,
-                                   float in_act_param) {
+                                   float in_act_param, const T* __restrict__ addend) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2, ncol = C / V;
   const int64_t total = (int64_t)N * Do * Ho * Wo * ncol;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -127,6 +127,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
 #pragma unroll
           for (int j = 0; j < V; ++j) g[j] = (inside && u.b[j] == code) ? gy[j] : 0.f;
           const int64_t off = ((((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dyy)) * W + (2 * ow + dxx)) * C + cv * V;
+          if (addend != nullptr) {
+            float a[V];
+            load_vec<T, V>(addend + off, a);
+#pragma unroll
+            for (int j = 0; j < V; ++j) g[j] += a[j];
+          }
           store_vec<T, V>(dx + off, g);
         }
   }
@@ -291,7 +297,7 @@ extern "C" int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stre
   MEDNET_DISPATCH_TV(p->dtype, V, {
     maxpool_bwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->dy, p->idx, (T*)p->dx, p->N, p->D,
                                                                        p->H, p->W, p->C, (const T*)p->y, p->in_act,
-                                                                       p->in_act_param);
+                                                                       p->in_act_param, (const T*)p->addend);
   });
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;

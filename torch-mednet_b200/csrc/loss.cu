@@ -49,6 +49,46 @@ __device__ __forceinline__ void voxel_probs(const T* __restrict__ base, int64_t 
   }
 }
 
+// same, from logits already held in registers (lets a kernel batch the loads of several voxels first)
+template <int CM>
+__device__ __forceinline__ void probs_inplace(int C, int sigmoid, float (&p)[CM]) {
+  if (sigmoid) {
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+      if (c < C) p[c] = 1.f / (1.f + expf(-p[c]));
+    return;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < CM; ++c)
+    if (c < C) mx = fmaxf(mx, p[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CM; ++c)
+    if (c < C) {
+      p[c] = expf(p[c] - mx);
+      sum += p[c];
+    }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int c = 0; c < CM; ++c)
+    if (c < C) p[c] *= inv;
+}
+
+// voxel index -> (sample, offset) without a 64-bit division when the tensor is small enough
+__device__ __forceinline__ void split_index(int64_t i, int64_t S, int64_t& n, int64_t& s) {
+  if (i < 0x7fffffffLL && S < 0x7fffffffLL) {
+    const uint32_t q = (uint32_t)i / (uint32_t)S;
+    n = q;
+    s = (int64_t)((uint32_t)i - q * (uint32_t)S);
+  } else {
+    n = i / S;
+    s = i - n * S;
+  }
+}
+
+constexpr int LOSS_UNR = 4;   // voxels per thread and iteration: their logits / labels are loaded before any arithmetic
+
 // block-reduce NV values; thread 0 writes them to out[0..NV)
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(float (&v)[NV], int nvalid, float* out) {
@@ -78,19 +118,36 @@ __global__ void dice_partial_kernel(const T* __restrict__ logits, const void* __
   float acc[3 * CM];
 #pragma unroll
   for (int i = 0; i < 3 * CM; ++i) acc[i] = 0.f;
-  const int64_t total = N * S;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = i / S, s = i - n * S;
-    float p[CM];
-    voxel_probs<T, CM>(logits + n * bstride + s, S, C, sigmoid, p);
-    const int y = load_label<TL>(labels, i);
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += LOSS_UNR * stride) {
+    float p[LOSS_UNR][CM];
+    int y[LOSS_UNR];
 #pragma unroll
-    for (int c = 0; c < CM; ++c) {
-      if (c < C) {
-        const float t = (y == c) ? 1.f : 0.f;
-        acc[c] += p[c] * t;
-        acc[CM + c] += p[c];
-        acc[2 * CM + c] += t;
+    for (int u = 0; u < LOSS_UNR; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        int64_t n, sv;
+        split_index(i, S, n, sv);
+        const T* base = logits + n * bstride + sv;
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+          if (c < C) p[u][c] = to_f32<T>(base[(int64_t)c * S]);
+        y[u] = load_label<TL>(labels, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LOSS_UNR; ++u) {
+      if (i0 + u * stride < total) {
+        probs_inplace<CM>(C, sigmoid, p[u]);
+#pragma unroll
+        for (int c = 0; c < CM; ++c) {
+          if (c < C) {
+            const float t = (y[u] == c) ? 1.f : 0.f;
+            acc[c] += p[u][c] * t;
+            acc[CM + c] += p[u][c];
+            acc[2 * CM + c] += t;
+          }
+        }
       }
     }
   }
@@ -143,27 +200,46 @@ __global__ void dice_bwd_kernel(const T* __restrict__ logits, const void* __rest
     sb[c] = (den >= eps) ? go * 2.f * w * sums[c] / (U * U) : 0.f;
   }
   __syncthreads();
-  const int64_t total = N * S;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = i / S, s = i - n * S;
-    float p[CM];
-    voxel_probs<T, CM>(logits + n * bstride + s, S, C, sigmoid, p);
-    const int y = load_label<TL>(labels, i);
-    float g[CM];
-    float dot = 0.f;
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += LOSS_UNR * stride) {
+    float p[LOSS_UNR][CM];
+    int y[LOSS_UNR];
+    int64_t off_out[LOSS_UNR];
 #pragma unroll
-    for (int c = 0; c < CM; ++c) {
-      if (c < C) {
-        g[c] = ((y == c) ? sa[c] : 0.f) + sb[c];
-        dot += p[c] * g[c];
+    for (int u = 0; u < LOSS_UNR; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        int64_t n, sv;
+        split_index(i, S, n, sv);
+        const T* base = logits + n * bstride + sv;
+        off_out[u] = n * bstride_out + sv;
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+          if (c < C) p[u][c] = to_f32<T>(base[(int64_t)c * S]);
+        y[u] = load_label<TL>(labels, i);
       }
     }
-    TO* out = dlogits + n * bstride_out + s;
 #pragma unroll
-    for (int c = 0; c < CM; ++c) {
-      if (c < C) {
-        const float dz = sigmoid ? g[c] * p[c] * (1.f - p[c]) : p[c] * (g[c] - dot);
-        out[(int64_t)c * S] = from_f32<TO>(dz);
+    for (int u = 0; u < LOSS_UNR; ++u) {
+      if (i0 + u * stride < total) {
+        probs_inplace<CM>(C, sigmoid, p[u]);
+        float g[CM];
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) {
+          if (c < C) {
+            g[c] = ((y[u] == c) ? sa[c] : 0.f) + sb[c];
+            dot += p[u][c] * g[c];
+          }
+        }
+        TO* out = dlogits + off_out[u];
+#pragma unroll
+        for (int c = 0; c < CM; ++c) {
+          if (c < C) {
+            const float dz = sigmoid ? g[c] * p[u][c] * (1.f - p[u][c]) : p[u][c] * (g[c] - dot);
+            out[(int64_t)c * S] = from_f32<TO>(dz);
+          }
+        }
       }
     }
   }

@@ -311,12 +311,12 @@ def k_pool_fwd(x):
     return y, idx
 
 
-def k_pool_bwd(dy, idx, in_shape, y=None, in_act=0):
+def k_pool_bwd(dy, idx, in_shape, y=None, in_act=0, addend=None):
     _need_cuda(dy, idx)
     n, d, h, w, c = in_shape
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
     p = make("mednet_pool_bwd_params", dy=_ptr(dy), idx=_ptr(idx), dx=_ptr(dx), N=n, D=d, H=h, W=w, C=c, dtype=_dt(dy),
-             y=_ptr(y), in_act=in_act, in_act_param=ACT_PARAM[in_act])
+             y=_ptr(y), in_act=in_act, in_act_param=ACT_PARAM[in_act], addend=_ptr(addend))
     check(lib().mednet_maxpool3d_bwd(_abi.C.byref(p), _stream()), "maxpool3d_bwd")
     _count()
     return dx
@@ -675,6 +675,28 @@ class MaxPoolFn(torch.autograd.Function):
     def backward(ctx, dy):
         idx, y = ctx.saved_tensors
         return k_pool_bwd(_c(dy), idx, ctx.in_shape, y, ctx.in_act), None
+
+
+class MaxPoolSkipFn(torch.autograd.Function):
+    """MaxPool3d(2) of an encoder output that ALSO feeds a skip connection: returns (pooled, x) and, in backward,
+    adds the skip path's gradient to the pool gradient inside the pool-backward kernel (one pass instead of autograd's
+    pool-backward + accumulate).  ref: components.py:210,224 and the encoder features kept at model.py:90-95."""
+
+    @staticmethod
+    def forward(ctx, x, in_act=0):
+        x = _c(x)
+        y, idx = k_pool_fwd(x)
+        ctx.save_for_backward(idx, y if in_act else None)
+        ctx.in_shape, ctx.in_act = tuple(x.shape), in_act
+        ctx.set_materialize_grads(False)                      # an unused branch arrives as None, not as a zeros tensor
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        idx, y = ctx.saved_tensors
+        if dy is None:
+            return dskip, None
+        return k_pool_bwd(_c(dy), idx, ctx.in_shape, y, ctx.in_act, _c(dskip) if dskip is not None else None), None
 
 
 class UpsampleConcatFn(torch.autograd.Function):

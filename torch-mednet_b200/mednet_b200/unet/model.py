@@ -56,26 +56,29 @@ class _UNetBase(LightningModule):
         convolutions skip their separate activation-backward pass (`defer`, see include/mednet_b200.h)."""
         x = to_ndhwc(x, self.cfg)
         blocks = [e.basic_module for e in self.encoders] + [d.basic_module for d in self.decoders]
-        defer = torch.is_grad_enabled() and all(getattr(b, 'out_act', 0) for b in blocks) and \
+        grad = torch.is_grad_enabled()
+        defer = grad and all(getattr(b, 'out_act', 0) for b in blocks) and \
             all(e.accepts_in_act() for e in self.encoders[1:]) and all(d.accepts_in_act() for d in self.decoders)
-        if not defer:
-            encoders_features = []
-            for encoder in self.encoders:
-                x = encoder.run(x)
-                encoders_features.insert(0, x)
-            encoders_features = encoders_features[1:]
-            for decoder, encoder_features in zip(self.decoders, encoders_features):
-                x = decoder.run(encoder_features, x)
-            return ops.Conv1x1Fn.apply(x, self.final_conv.weight, self.final_conv.bias)
         feats, acts, act = [], [], 0
-        for encoder in self.encoders:
-            x = encoder.run(x, in_act=act, defer=True)
-            act = encoder.basic_module.out_act
+        for i, encoder in enumerate(self.encoders):
+            if i > 0 and grad and encoder.pooling is not None and len(self.decoders) > 0:
+                # x feeds both this encoder's pool and a decoder's join: one fused backward for the two gradients
+                pooled, skip = ops.MaxPoolSkipFn.apply(x, act)
+                feats[0] = skip
+                x = encoder.basic_module.run(pooled, defer=True) if defer else encoder.basic_module.run(pooled)
+            elif defer:
+                x = encoder.run(x, in_act=act, defer=True)
+            else:
+                x = encoder.run(x)
+            act = encoder.basic_module.out_act if defer else 0
             feats.insert(0, x)
             acts.insert(0, act)
         for decoder, skip, skip_act in zip(self.decoders, feats[1:], acts[1:]):
-            x = decoder.run(skip, x, skip_act=skip_act, x_act=act, defer=True)
-            act = decoder.basic_module.out_act
+            if defer:
+                x = decoder.run(skip, x, skip_act=skip_act, x_act=act, defer=True)
+                act = decoder.basic_module.out_act
+            else:
+                x = decoder.run(skip, x)
         return ops.Conv1x1Fn.apply(x, self.final_conv.weight, self.final_conv.bias, act)
 
 
