@@ -43,6 +43,10 @@ WORKLOADS = {
                  desc="wide UNet3D f=[32..512] 5-level, batch 2 per GPU, 160^3, Dice"),
     "tiny": dict(arch="unet3d", f_maps=[16, 32, 64], classes=2, heatmaps=0, batch=2, edge=32, loss="DICE",
                  desc="smoke-sized UNet3D"),
+    # sliding-window inference (examples/predict.py): not the headline metric, measured with --workload cfg4
+    "cfg4": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=4, edge=128, loss="DICE", predict=True,
+                 volume=(512, 512, 400), overlap=16,
+                 desc="sliding-window inference, 512x512x400 volume, 128^3 tiles, overlap 16 (180 tiles), tile batch 4"),
 }
 
 
@@ -172,6 +176,64 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ predict arm
+def run_predict(args, wl):
+    """cfg-4: tiles sharded round-robin over the ranks, no data-path collective; one "step" = the whole volume.
+    value = USEFUL output voxels / s (the BASELINE.json 'predict voxels/s'); computed voxels/s reported beside it."""
+    import numpy as np
+    import torch.distributed as dist
+    from mednet_b200.parallel import init_distributed
+    from mednet_b200.predict import SlidingWindowPredictor
+    from mednet_b200.segmentation import SegmentationUNet3D
+    rank, local, world = init_distributed()
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    model = SegmentationUNet3D(hparams_for(wl)).to(dev)
+    model.freeze()
+    X, Y, Z = wl["volume"]
+    vol_host = torch.randn((1, X, Y, Z), generator=torch.Generator().manual_seed(7)).to(torch.bfloat16).pin_memory()
+    vol_dev = vol_host.to(dev)
+    pred = SlidingWindowPredictor(model, [wl["edge"]] * 3, [wl["overlap"]] * 3, wl["heatmaps"], wl["batch"], rank, world)
+    tiles = len(pred.tile_origins((X, Y, Z)))
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    steps, warm = max(1, min(args.steps, 3)), 1
+    for _ in range(warm):
+        pred(vol_dev)
+    ms = timed(lambda: pred(vol_dev), steps)
+    ms_e2e = timed(lambda: pred(vol_host).cpu(), steps)        # host volume in, stitched uint8 volume back on the host
+    if rank == 0:
+        useful = X * Y * Z
+        line = {"metric": "UNet3D predict voxels/s", "value": useful * steps / (ms * 1e-3), "unit": "voxels/s",
+                "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": args.workload + ": " + wl["desc"], "tiles": tiles,
+                           "computed_voxels_per_s": tiles * wl["edge"] ** 3 * steps / (ms * 1e-3),
+                           "l2": "inputs larger than L2"},
+                "e2e": {"value": useful * steps / (ms_e2e * 1e-3), "unit": "voxels/s",
+                        "h2d_bytes_per_step": vol_host.numel() * 2, "d2h_bytes_per_step": (wl["heatmaps"] + 1) * useful,
+                        "ms_per_step": ms_e2e / steps}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +247,9 @@ def main():
     ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if wl.get("predict"):
+        run_predict(args, wl)
+        return
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return

@@ -95,7 +95,12 @@ WGRAD_CASES = [
     (1, 128, 128, (3, 9, 9)),
     (1, 384, 128, (2, 8, 8)),       # U = X, 3 U tiles, 4 S chunks
     (2, 256, 512, (1, 5, 7)),       # depth 1 (TD = 1), U = dY 512
-    (1, 64, 96, (2, 16, 8)),        # S = X 64 ch, U = dY 96?? -> 96 % 64 != 0: must be refused (SIMT)
+    (1, 16, 32, (4, 16, 8)),        # cfg-5 first level: U = dY 32 (3/4 of M zero-filled), S = X 16 (half a chunk)
+    (2, 32, 32, (3, 10, 9)),
+    (1, 96, 32, (2, 16, 8)),        # U = X 96 = 64 + 32
+    (1, 24, 40, (2, 8, 8)),         # multiples of 8 only
+    (1, 64, 96, (2, 16, 8)),        # U = dY 96 = 64 + 32 (second atom half filled)
+    (1, 20, 36, (2, 8, 8)),         # not multiples of 8: must be refused (CUDA-core kernel)
 ]
 
 
@@ -119,10 +124,10 @@ def test_wgrad_tcgen05_exact_on_integer_data(n, cin, cout, shape):
     p = ops.wgrad_params(dg, xg, 0, "auto")
     impl = ops.lib().mednet_conv3d_wgrad_select_impl(ops._abi.C.byref(p))
     cu, cs = (cin, cout) if cin > cout else (cout, cin)       # U = the operand with more channels, S = the other
-    if cu % 64 != 0 or cs % 32 != 0:
+    if cu % 8 != 0 or cs % 8 != 0 or cs <= 4:
         assert impl == 1                                      # refused by the tensor-core planner -> CUDA-core kernel
         return
-    assert impl == 2, "bf16 wgrad with 64/32-aligned channels must run on the tensor cores"
+    assert impl == 2, "bf16 wgrad with 8-aligned channels must run on the tensor cores"
     dw, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
     torch.cuda.synchronize()
     ref = _wgrad_ref(x, dy)

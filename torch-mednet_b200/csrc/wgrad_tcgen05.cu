@@ -230,13 +230,15 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   // U = the operand with more channels (ties: dY); S = the other one, in chunks of 32 channels
   pl.u_is_x = q->Cb > q->Ca ? 1 : 0;
   const int CU = pl.u_is_x ? q->Cb : q->Ca, CSn = pl.u_is_x ? q->Ca : q->Cb;
-  if (CU % 64 != 0 || CSn % CS != 0) return false;
+  // any multiple of 8 channels (16-byte global strides): TMA boxes reaching past the channel extent are zero-filled, so a
+  // 32- or 96-channel U simply leaves rows of the 128-row accumulator empty and a 16-channel S leaves columns empty
+  if (CU % 8 != 0 || CSn % 8 != 0) return false;
   WgArgs& a = pl.a;
   a.N = q->N; a.D = q->Da; a.H = q->Ha; a.W = q->Wa; a.CU = CU; a.CSn = CSn;
   a.TD = q->Da >= 2 ? 2 : 1;
   a.tiles_d = ceil_div(a.D, a.TD); a.tiles_h = ceil_div(a.H, BR_H); a.tiles_w = ceil_div(a.W, BR_W);
   a.bricks = (int64_t)a.N * a.tiles_d * a.tiles_h * a.tiles_w;
-  a.u_tiles = ceil_div(CU, 128); a.s_chunks = CSn / CS;
+  a.u_tiles = ceil_div(CU, 128); a.s_chunks = ceil_div(CSn, CS);
   const int worktypes = a.u_tiles * a.s_chunks * 2;
   const int sms = sm_count_cached();
   int64_t ksplit = (2 * sms + worktypes - 1) / worktypes;       // ~2 CTAs per SM in total: bounded tail
