@@ -43,6 +43,9 @@ WORKLOADS = {
                  desc="wide UNet3D f=[32..512] 5-level, batch 2 per GPU, 160^3, Dice"),
     "tiny": dict(arch="unet3d", f_maps=[16, 32, 64], classes=2, heatmaps=0, batch=2, edge=32, loss="DICE",
                  desc="smoke-sized UNet3D"),
+    # the network the reference's task modules actually derive from (segmentation.py:22): not the headline metric
+    "res32": dict(arch="residual", f_maps=32, classes=2, heatmaps=0, batch=2, edge=128, loss="DICE",
+                  desc="ResidualUNet3D(1,2) f=32 5-level (SegmentationNet as shipped), batch 2, 128^3, Dice"),
     # sliding-window inference (examples/predict.py): not the headline metric, measured with --workload cfg4
     "cfg4": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=4, edge=128, loss="DICE", predict=True,
                  volume=(512, 512, 400), overlap=16,
@@ -97,17 +100,18 @@ def cpu_oracle_voxels_per_s(wl, steps, warmup, edge=None, batch=None):
     batch = batch or wl["batch"]
     sub = dict(wl, edge=edge, batch=batch)
     out_ch = wl["classes"] + wl["heatmaps"]
-    sd = ounet.make_unet3d_state_dict(1, out_ch, wl["f_maps"])
+    kind = "residual" if wl["arch"] == "residual" else "unet3d"
+    sd = (ounet.make_residual_unet3d_state_dict if kind == "residual" else ounet.make_unet3d_state_dict)(1, out_ch, wl["f_maps"])
     b = synthetic_batch(sub, 0, "cpu")
     kw = dict(f_maps=wl["f_maps"])
     if wl["heatmaps"]:
         hp = hparams_for(wl)
-        times, _ = osteps.time_training_steps("unet3d", sd, b, steps=steps, warmup=warmup, task="ldmk",
+        times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="ldmk",
                                               loss_class=hp.loss_class, loss_class_weight=hp.loss_class_weight,
                                               loss_regression_weight=hp.loss_regression_weight, **kw)
     else:
         hp = hparams_for(wl)
-        times, _ = osteps.time_training_steps("unet3d", sd, b, steps=steps, warmup=warmup, task="seg", loss=hp.loss,
+        times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="seg", loss=hp.loss,
                                               loss_weight=hp.loss_weight, **kw)
     t = sum(times) / len(times)
     vox = batch * edge ** 3
@@ -258,9 +262,9 @@ def main():
 
     import torch.distributed as dist
     from mednet_b200 import ops
-    from mednet_b200.landmarks import LandmarkUNet3D
+    from mednet_b200.landmarks import LandmarkNet, LandmarkUNet3D
     from mednet_b200.parallel import BucketedAllReduce, init_distributed
-    from mednet_b200.segmentation import SegmentationUNet3D
+    from mednet_b200.segmentation import SegmentationNet, SegmentationUNet3D
 
     rank, local, world = init_distributed()
     dev = torch.device("cuda", local)
@@ -268,7 +272,10 @@ def main():
     from mednet_b200._abi import check, lib
     check(lib().mednet_tcgen05_set_option(b"dual_issue", args.dual_issue), "tcgen05_set_option")
     hp = hparams_for(wl)
-    cls = LandmarkUNet3D if wl["heatmaps"] else SegmentationUNet3D
+    if wl["arch"] == "residual":
+        cls = LandmarkNet if wl["heatmaps"] else SegmentationNet
+    else:
+        cls = LandmarkUNet3D if wl["heatmaps"] else SegmentationUNet3D
     model = cls(hp, conv_impl=args.conv_impl).to(dev)
     opt = model.configure_optimizers()
     reducer = BucketedAllReduce(opt.grad_slices(), opt.flat_grad) if world > 1 else None

@@ -53,6 +53,8 @@ typedef struct CUstream_st* mednet_stream_t;
 #define MEDNET_WPACK_SIMT_DGRAD    1   /* [Cin][27 flipped][Cout]     */
 #define MEDNET_WPACK_TC_FPROP      2   /* [27][Cout][Cin]            */
 #define MEDNET_WPACK_TC_DGRAD      3   /* [27 flipped][Cin][Cout]     */
+#define MEDNET_WPACK_TC_CONVT_F    4   /* transposed conv fprop: [8 parity classes][27 window taps][Cout][Cin] (8*27*Cin*Cout) */
+#define MEDNET_WPACK_TC_CONVT_B    5   /* transposed conv dgrad: [8 parity classes][27 window taps][Cin][Cout]                 */
 
 /* gather modes of the generic implicit GEMM */
 #define MEDNET_GATHER_CONV3   0   /* 3x3x3, stride 1, pad 1               */

@@ -156,3 +156,31 @@ def test_wgrad_tcgen05_is_deterministic():
     a, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
     b, _ = ops.k_wgrad(dg, xg, 0, "tcgen05")
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(32, 16, (4, 16, 8)), (64, 32, (3, 9, 11)), (128, 64, (2, 5, 6)), (16, 16, (5, 4, 3))])
+def test_conv_transpose_tcgen05_exact_on_integer_data(cin, cout, shape):
+    """ConvTranspose3d(k3, s2, p1, op1) + bias + skip sum on the tensor cores (8 parity classes of 1/2/4/8 taps;
+    dgrad through a stride-2 TMA map) -- small-integer operands make every product and fp32 sum exact, so forward and
+    input gradient must equal F.conv_transpose3d bit for bit after the bf16 rounding of the OUTPUT.
+    ref: midasmednet/unet/components.py:259-264, 283-284."""
+    torch.manual_seed(cin + cout)
+    x = torch.randint(-2, 3, (2, cin) + shape).float().requires_grad_()
+    w = torch.randint(-1, 2, (cin, cout, 3, 3, 3)).float().requires_grad_()
+    b = torch.randint(-2, 3, (cout,)).float()
+    big = tuple(2 * s for s in shape)
+    skip = torch.randint(-2, 3, (2, cout) + big).float()
+    ref = F.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1) + skip
+    g = torch.randint(-1, 2, ref.shape).float()
+    ref.backward(g)
+    nd = lambda t: t.permute(0, 2, 3, 4, 1).contiguous().to(DEV, torch.bfloat16)
+    xg = nd(x.detach()).requires_grad_()
+    wg, bg = w.detach().to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
+    assert ops.conv_select_impl(xg.shape, big, cin, cout, xg.dtype, 1, "auto", xg.data_ptr()) == 2
+    y = ops.ConvTranspose3x3Fn.apply(xg, wg, bg, nd(skip), "auto")
+    y.backward(nd(g))
+    back = lambda t: t.float().permute(0, 4, 1, 2, 3).cpu()
+    assert torch.equal(back(y.detach()), ref.detach().bfloat16().float())
+    assert torch.equal(back(xg.grad), x.grad.bfloat16().float())
+    assert relerr(wg.grad.cpu(), w.grad) < 1e-5
+    assert relerr(bg.grad.cpu(), g.sum(dim=(0, 2, 3, 4))) < 1e-6

@@ -298,6 +298,39 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// Packed weights of the transposed convolution for the tensor-core kernel: one [27][Nout][K] set per parity class,
+// indexed by WINDOW tap (offset + 1 per axis); inactive taps are zero (never loaded).  src is the ConvTranspose3d
+// weight (Cin, Cout, 3, 3, 3).  k3 s2 p1 op1: o = 2i - 1 + k.
+//   fprop  (dgrad = 0): y[2j + par] += x[j + off] W[k]:  par 0: (off 0, k 1);  par 1: (off 0, k 2), (off +1, k 0)
+//   dgrad  (dgrad = 1): dx[i] += dy[2(i + off) + par] W[k]^T:  par 0: (off 0, k 1);  par 1: (off -1, k 0), (off 0, k 2)
+template <typename T>
+__global__ void pack_weights_convt_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cin, int Cout, int dgrad) {
+  const int Nout = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
+  const int64_t total = (int64_t)8 * 27 * Nout * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int nout = (int)((i / K) % Nout);
+    const int tap = (int)((i / ((int64_t)K * Nout)) % 27);
+    const int cls = (int)(i / ((int64_t)K * Nout * 27));
+    const int kk[3] = {tap / 9, (tap / 3) % 3, tap % 3}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+    int ksrc[3];
+    bool on = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int off = kk[a] - 1;
+      if (par[a] == 0) { on = on && off == 0; ksrc[a] = 1; }
+      else if (!dgrad) { on = on && off >= 0; ksrc[a] = off == 0 ? 2 : 0; }
+      else { on = on && off <= 0; ksrc[a] = off == 0 ? 2 : 0; }
+    }
+    float v = 0.f;
+    if (on) {
+      const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
+      v = src[((int64_t)ci * Cout + co) * 27 + (ksrc[0] * 3 + ksrc[1]) * 3 + ksrc[2]];
+    }
+    dst[i] = from_f32<T>(v);
+  }
+}
+
 int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int accumulate, void* workspace,
                 cudaStream_t st);
 
@@ -865,7 +898,20 @@ using namespace mednet;
 extern "C" int mednet_conv3d_pack_weights(const mednet_wpack_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->w_oidhw && p->w_packed && p->Cin > 0 && p->Cout > 0, MEDNET_EINVAL);
   MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
-  MEDNET_REQUIRE(p->layout >= 0 && p->layout <= 3, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->layout >= 0 && p->layout <= 5, MEDNET_EINVAL);
+  if (p->layout >= MEDNET_WPACK_TC_CONVT_F) {
+    MEDNET_REQUIRE(p->transposed, MEDNET_EINVAL);
+    const int dg = p->layout == MEDNET_WPACK_TC_CONVT_B ? 1 : 0;
+    const int64_t tot = (int64_t)8 * 27 * p->Cin * p->Cout;
+    if (p->dtype == MEDNET_F32)
+      pack_weights_convt_kernel<float><<<grid_for(tot, 256), 256, 0, stream>>>((const float*)p->w_oidhw, (float*)p->w_packed,
+                                                                              p->Cin, p->Cout, dg);
+    else
+      pack_weights_convt_kernel<bf16><<<grid_for(tot, 256), 256, 0, stream>>>((const float*)p->w_oidhw, (bf16*)p->w_packed,
+                                                                             p->Cin, p->Cout, dg);
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  }
   const int dgrad = p->layout & 1, tapmajor = p->layout >> 1;
   const int64_t total = (int64_t)p->Cin * p->Cout * 27;
   if (p->dtype == MEDNET_F32)

@@ -60,6 +60,13 @@ struct TcConv {
   int TD, Ntile, nchunks, RB, pitch, per_row, bo_mode;
   int plane_bytes, b_bytes, BS, acc_stages, tmem_cols;
   int dual;                    // 1: two MMA-issuing threads, each owning half of the brick's d-planes
+  // Parity classes of the stride-2 transposed convolution (components.py:259-264).  A plain conv has one class with all
+  // 27 taps.  Transposed fprop: 8 OUTPUT classes (output voxel = 2j + parity), each a sub-conv over the input grid with
+  // 1/2/4/8 taps; transposed dgrad: 8 INPUT classes (A read at 2j + parity through a stride-2 TMA map) accumulated into
+  // the same TMEM tile.  Window tap index = offset + 1 per axis, exactly as for the plain conv.
+  int ncls_in, ncls_out, in_scale, out_scale;
+  int OD, OH, OW;              // dims of the output tensor (= out_scale * grid)
+  uint32_t tapmask[8];
   int act;
   float act_param;
   const float* bias;
@@ -68,11 +75,12 @@ struct TcConv {
 };
 
 struct TileCoord {
-  int n, d0, h0, w0, n0;
+  int n, d0, h0, w0, n0, cls;
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcConv& p, int64_t t) {
   TileCoord c;
   c.n0 = (int)(t % p.tiles_n) * p.Ntile; t /= p.tiles_n;
+  c.cls = (int)(t % p.ncls_out); t /= p.ncls_out;     // the output classes of one brick run together: they share the halo in L2
   c.w0 = (int)(t % p.tiles_w) * TILE_W; t /= p.tiles_w;
   c.h0 = (int)(t % p.tiles_h) * TILE_H; t /= p.tiles_h;
   c.d0 = (int)(t % p.tiles_d) * p.TD;
@@ -103,10 +111,12 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
     tc::mbar_wait(&acc_full[as], aph);
     tc::tc_fence_after();
     const int h = tc_.h0 + hh, w = tc_.w0 + ww;
+    const int oh = p.out_scale * h + ((tc_.cls >> 1) & 1), ow = p.out_scale * w + (tc_.cls & 1);
     for (int dz = 0; dz < p.TD; ++dz) {
       const int d = tc_.d0 + dz;
       const bool inb = d < p.D && h < p.H && w < p.W;
-      const int64_t vox = (((int64_t)tc_.n * p.D + d) * p.H + h) * p.W + w;
+      const int od = p.out_scale * d + (tc_.cls >> 2);
+      const int64_t vox = (((int64_t)tc_.n * p.OD + od) * p.OH + oh) * p.OW + ow;
       bf16* yrow = p.y + vox * p.Nout + tc_.n0;
       const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
@@ -193,17 +203,21 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       uint32_t ait = 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, t);
-        for (int c = 0; c < p.nchunks; ++c, ++ait) {
-          for (int pl = 0; pl < nplanes; ++pl) {
-            tc::mbar_wait(&a_empty[pl], (ait & 1u) ^ 1u);
-            tc::mbar_arrive_expect_tx(&a_full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
-            uint8_t* dst = a_base + (size_t)pl * p.plane_bytes;
-            if (p.per_row) {
-              for (int ph = 0; ph < HALO_H; ++ph)
-                tc::tma_load_5d(dst + (size_t)ph * p.pitch * p.RB, &map_x, &a_full[pl], c * KC, tc_.w0 - 1,
-                                tc_.h0 - 1 + ph, tc_.d0 - 1 + pl, tc_.n);
-            } else {
-              tc::tma_load_5d(dst, &map_x, &a_full[pl], c * KC, tc_.w0 - 1, tc_.h0 - 1, tc_.d0 - 1 + pl, tc_.n);
+        for (int ci = 0; ci < p.ncls_in; ++ci) {
+          const int s = p.in_scale;
+          const int cw = s * (tc_.w0 - 1) + (ci & 1), ch = s * (tc_.h0 - 1) + ((ci >> 1) & 1), cd0 = s * (tc_.d0 - 1) + (ci >> 2);
+          for (int c = 0; c < p.nchunks; ++c, ++ait) {
+            for (int pl = 0; pl < nplanes; ++pl) {
+              tc::mbar_wait(&a_empty[pl], (ait & 1u) ^ 1u);
+              tc::mbar_arrive_expect_tx(&a_full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
+              uint8_t* dst = a_base + (size_t)pl * p.plane_bytes;
+              if (p.per_row) {
+                for (int ph = 0; ph < HALO_H; ++ph)
+                  tc::tma_load_5d(dst + (size_t)ph * p.pitch * p.RB, &map_x, &a_full[pl], c * KC, cw, ch + s * ph,
+                                  cd0 + s * pl, tc_.n);
+              } else {
+                tc::tma_load_5d(dst, &map_x, &a_full[pl], c * KC, cw, ch, cd0 + s * pl, tc_.n);
+              }
             }
           }
         }
@@ -215,12 +229,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       uint32_t bit = 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, t);
-        for (int c = 0; c < p.nchunks; ++c) {
-          for (int tap = 0; tap < 27; ++tap, ++bit) {
-            const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
-            tc::mbar_wait(&b_empty[st], ph ^ 1u);
-            tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(p.Ntile * p.RB));
-            tc::tma_load_2d(b_base + (size_t)st * p.b_bytes, &map_w, &b_full[st], c * KC, tap * p.Nout + tc_.n0);
+        for (int ci = 0; ci < p.ncls_in; ++ci) {
+          const int wcls = p.ncls_out > 1 ? tc_.cls : ci;          // weight set / tap mask of this (tile, input class)
+          const uint32_t mask = p.tapmask[wcls];
+          for (int c = 0; c < p.nchunks; ++c) {
+            for (int tap = 0; tap < 27; ++tap) {
+              if (!((mask >> tap) & 1u)) continue;
+              const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
+              ++bit;
+              tc::mbar_wait(&b_empty[st], ph ^ 1u);
+              tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(p.Ntile * p.RB));
+              tc::tma_load_2d(b_base + (size_t)st * p.b_bytes, &map_w, &b_full[st], c * KC,
+                              (wcls * 27 + tap) * p.Nout + tc_.n0);
+            }
           }
         }
       }
@@ -257,46 +278,54 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc::mbar_wait(&acc_empty[as], aph ^ 1u);
         tc::tc_fence_after();
         const uint32_t d_tile = tmem_base + as * (uint32_t)(p.TD * p.Ntile) + d_issuer;
-        for (int c = 0; c < p.nchunks; ++c, ++ait) {
-          for (int kd = 0; kd < 3; ++kd) {
-            if (kd == 0) {
-              for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full[pl], ait & 1u);
-            } else {
-              tc::mbar_wait(&a_full[p.TD - 1 + kd], ait & 1u);
-            }
-            tc::tc_fence_after();
-            const uint32_t a_kd = a_lo0 + (uint32_t)kd * plane16;
-#pragma unroll
-            for (int khw = 0; khw < 9; ++khw) {
-              tc::mbar_wait(&b_full[bst], bph);
-              tc::tc_fence_after();
-              const uint32_t b_lo = b_lo0 + bst * b16;
-              uint32_t a_lo = a_kd + tapoff[khw];
-              uint32_t d_tmem = d_tile;
-              const uint32_t first = (uint32_t)(c | kd | khw);
-              for (int dz = 0; dz < TDI; ++dz) {
-                if (ksteps == 4) {
-                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
-                  tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-                  tc::umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
-                  tc::umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
-                } else if (ksteps == 2) {
-                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
-                  tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-                } else {
-                  tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
-                }
-                a_lo += plane16;
-                d_tmem += (uint32_t)p.Ntile;
+        const int out_cls = p.ncls_out > 1 ? decode_tile(p, t).cls : -1;
+        uint32_t fresh = 1u;                              // the first MMA into each accumulator overwrites it
+        for (int ci = 0; ci < p.ncls_in; ++ci) {
+          const uint32_t mask = p.tapmask[out_cls >= 0 ? out_cls : ci];
+          for (int c = 0; c < p.nchunks; ++c, ++ait) {
+            for (int kd = 0; kd < 3; ++kd) {
+              if (kd == 0) {
+                for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full[pl], ait & 1u);
+              } else {
+                tc::mbar_wait(&a_full[p.TD - 1 + kd], ait & 1u);
               }
-              tc::umma_commit(&b_empty[bst]);
-              if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
-            }
-            // planes whose last tap phase is this kd can be refilled for the next chunk
-            if (kd < 2) {
-              tc::umma_commit(&a_empty[kd]);
-            } else {
-              for (int pl = 2; pl < nplanes; ++pl) tc::umma_commit(&a_empty[pl]);
+              tc::tc_fence_after();
+              const uint32_t a_kd = a_lo0 + (uint32_t)kd * plane16;
+              const uint32_t mask_kd = (mask >> (kd * 9)) & 0x1ffu;
+#pragma unroll
+              for (int khw = 0; khw < 9; ++khw) {
+                if (!((mask_kd >> khw) & 1u)) continue;
+                tc::mbar_wait(&b_full[bst], bph);
+                tc::tc_fence_after();
+                const uint32_t b_lo = b_lo0 + bst * b16;
+                uint32_t a_lo = a_kd + tapoff[khw];
+                uint32_t d_tmem = d_tile;
+                const uint32_t first = fresh ? 0u : 1u;
+                fresh = 0u;
+                for (int dz = 0; dz < TDI; ++dz) {
+                  if (ksteps == 4) {
+                    tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                    tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                    tc::umma_bf16_lohi(d_tmem, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                    tc::umma_bf16_lohi(d_tmem, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                  } else if (ksteps == 2) {
+                    tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                    tc::umma_bf16_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  } else {
+                    tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                  }
+                  a_lo += plane16;
+                  d_tmem += (uint32_t)p.Ntile;
+                }
+                tc::umma_commit(&b_empty[bst]);
+                if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
+              }
+              // planes whose last tap phase is this kd can be refilled for the next chunk
+              if (kd < 2) {
+                tc::umma_commit(&a_empty[kd]);
+              } else {
+                for (int pl = 2; pl < nplanes; ++pl) tc::umma_commit(&a_empty[pl]);
+              }
             }
           }
         }
@@ -332,13 +361,37 @@ static int pick_row_bytes(int K) { return (K % 64 == 0) ? 128 : (K % 32 == 0) ? 
 
 static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   TcConv p;
-  p.N = q->N; p.D = q->Do; p.H = q->Ho; p.W = q->Wo; p.K = q->K; p.Nout = q->Nout;
+  // the tile grid is the SMALLER of the two volumes for the transposed conv (its 8 parity classes tile the other one)
+  const bool tf = q->gather == MEDNET_GATHER_CONVT_F, tb = q->gather == MEDNET_GATHER_CONVT_B;
+  p.N = q->N; p.K = q->K; p.Nout = q->Nout;
+  p.D = tf ? q->Di : q->Do; p.H = tf ? q->Hi : q->Ho; p.W = tf ? q->Wi : q->Wo;
+  p.OD = q->Do; p.OH = q->Ho; p.OW = q->Wo;
+  p.ncls_in = tb ? 8 : 1; p.ncls_out = tf ? 8 : 1;
+  p.in_scale = tb ? 2 : 1; p.out_scale = tf ? 2 : 1;
+  if (tf && (q->Do != 2 * q->Di || q->Ho != 2 * q->Hi || q->Wo != 2 * q->Wi)) return false;
+  if (tb && (q->Di != 2 * q->Do || q->Hi != 2 * q->Ho || q->Wi != 2 * q->Wo)) return false;
+  for (int cls = 0; cls < 8; ++cls) {
+    // window tap index = offset + 1 per axis.  plain conv: offsets -1..1.  transposed fprop, output parity 1: offsets
+    // {0, +1}; transposed dgrad, input parity 1: offsets {-1, 0}; parity 0: offset 0 only (components.py:259-264:
+    // k3 s2 p1 op1 -> o = 2i - 1 + k)
+    uint32_t m = 0;
+    for (int tap = 0; tap < 27; ++tap) {
+      const int kk[3] = {tap / 9, (tap / 3) % 3, tap % 3}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+      bool on = true;
+      for (int a = 0; a < 3; ++a) {
+        if (tf) on = on && (par[a] ? kk[a] >= 1 : kk[a] == 1);
+        else if (tb) on = on && (par[a] ? kk[a] <= 1 : kk[a] == 1);
+      }
+      if (on) m |= 1u << tap;
+    }
+    p.tapmask[cls] = m;
+  }
   p.RB = pick_row_bytes(q->K);
   p.Ntile = pick_ntile(q->Nout);
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
   p.nchunks = q->K / (p.RB / 2);
   // more planes per brick = fewer halo re-reads and weight-tile loads per voxel; TMEM holds TD * Ntile columns per stage
-  p.TD = (p.Ntile <= 64 && q->Do >= 4) ? 4 : (q->Do >= 2 ? 2 : 1);
+  p.TD = (p.Ntile <= 64 && p.D >= 4) ? 4 : (p.D >= 2 ? 2 : 1);
   const int rc = rb_class(p.RB);
   if (!g_enabled[rc] || g_base_offset_mode[rc] != 0) return false;   // the kernel issues base_offset = 0 descriptors
   p.per_row = g_dense_halo[rc] ? 0 : 1;
@@ -361,7 +414,8 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   p.tiles_h = ceil_div(p.H, TILE_H);
   p.tiles_d = ceil_div(p.D, p.TD);
   p.tiles_n = q->Nout / p.Ntile;
-  p.num_tiles = (int64_t)p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.num_tiles = (int64_t)p.N * p.tiles_d * p.tiles_h * p.tiles_w * p.tiles_n * p.ncls_out;
+  if ((tf || tb) && p.per_row) return false;          // strided halo boxes are implemented for the dense halo only
   p.act = q->act; p.act_param = q->act_param;
   p.bias = q->bias; p.addend = (const bf16*)q->addend; p.y = (bf16*)q->y;
   *out = p;
@@ -369,7 +423,8 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
 }
 
 bool tc_fprop_supported(const mednet_conv3d_params* q) {
-  if (q->dtype != MEDNET_BF16 || q->gather != MEDNET_GATHER_CONV3) return false;
+  if (q->dtype != MEDNET_BF16) return false;
+  if (q->gather != MEDNET_GATHER_CONV3 && q->gather != MEDNET_GATHER_CONVT_F && q->gather != MEDNET_GATHER_CONVT_B) return false;
   if (!mednet_device_has_tcgen05()) return false;
   if (((uintptr_t)q->x | (uintptr_t)q->w | (uintptr_t)q->y | (uintptr_t)q->addend | (uintptr_t)q->bias) & 15) return false;
   TcConv p;
@@ -384,18 +439,22 @@ int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
   const int KC = p.RB / 2;
   CUtensorMap map_x, map_w;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)p.K, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
-    cuuint64_t strides[4] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.W * p.K * 2, (cuuint64_t)p.H * p.W * p.K * 2,
-                             (cuuint64_t)p.D * p.H * p.W * p.K * 2};
-    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)HALO_W, (cuuint32_t)(p.per_row ? 1 : HALO_H), 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    // A is read from the INPUT tensor (q->Di..); transposed dgrad reads every second voxel (traversal stride 2: the box
+    // spans 2 * halo elements and lands as halo elements in shared memory), the parity is in the start coordinate
+    const cuuint64_t XD = (cuuint64_t)q->Di, XH = (cuuint64_t)q->Hi, XW = (cuuint64_t)q->Wi;
+    const cuuint32_t es = (cuuint32_t)p.in_scale;
+    cuuint64_t dims[5] = {(cuuint64_t)p.K, XW, XH, XD, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)p.K * 2, XW * p.K * 2, XH * XW * p.K * 2, XD * XH * XW * p.K * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)HALO_W * es, (cuuint32_t)(p.per_row ? 1 : HALO_H * es), 1, 1};
+    cuuint32_t estr[5] = {1, es, p.per_row ? 1u : es, 1, 1};
     if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(q->x), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(p.RB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MEDNET_EUNSUPPORTED;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)27 * p.Nout};
+    const int wsets = p.ncls_in > 1 ? p.ncls_in : p.ncls_out;       // one [27][Nout][K] weight set per parity class
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)27 * p.Nout * wsets};
     cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)p.Ntile};
     cuuint32_t estr[2] = {1, 1};

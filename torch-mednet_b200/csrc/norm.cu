@@ -249,19 +249,25 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const 
   const int cpg = C / G;
   const double mu = (double)mean[n * G + g], rs = (double)rstd[n * G + g];
   double ds = 0.0, db = 0.0;
-  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+  // one warp per channel of the group, lanes stride over the slabs (fixed order: deterministic)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < cpg; i += nw) {
     const int c = g * cpg + i;
     double s1 = 0.0, s2x = 0.0;
-    for (int slab = 0; slab < nslab; ++slab) {
+    for (int slab = lane; slab < nslab; slab += 32) {
       const float* p = partial + ((int64_t)n * nslab + slab) * 2 * C;
       s1 += (double)p[c];
       s2x += (double)p[C + c];
     }
-    const double s2 = rs * (s2x - mu * s1);
-    dgb[((int64_t)n * 2 + 0) * C + c] = (float)s2;
-    dgb[((int64_t)n * 2 + 1) * C + c] = (float)s1;
-    ds += (double)gamma[c] * s2;
-    db += (double)gamma[c] * s1;
+    s1 = warp_sum(s1);
+    s2x = warp_sum(s2x);
+    if (lane == 0) {
+      const double s2 = rs * (s2x - mu * s1);
+      dgb[((int64_t)n * 2 + 0) * C + c] = (float)s2;
+      dgb[((int64_t)n * 2 + 1) * C + c] = (float)s1;
+      ds += (double)gamma[c] * s2;
+      db += (double)gamma[c] * s1;
+    }
   }
   ds = block_sum(ds, scratch);
   db = block_sum(db, scratch);

@@ -159,7 +159,7 @@ def conv_select_impl(x_shape, out_sp, K, Nout, dtype, gather, impl, x_ptr=0, w_p
 def k_pack_weights(w, cin, cout, dtype, layout, transposed=False):
     _need_cuda(w)
     w = w.detach().contiguous().float()
-    out = torch.empty(cin * cout * 27, dtype=dtype, device=w.device)
+    out = torch.empty(cin * cout * 27 * (8 if layout >= 4 else 1), dtype=dtype, device=w.device)
     p = make("mednet_wpack_params", w_oidhw=_ptr(w), w_packed=_ptr(out), Cin=cin, Cout=cout, dtype=_DT[dtype],
              layout=layout, transposed=int(transposed))
     check(lib().mednet_conv3d_pack_weights(_abi.C.byref(p), _stream()), "conv3d_pack_weights")
@@ -584,8 +584,10 @@ class ConvTranspose3x3Fn(torch.autograd.Function):
         if skip is not None and tuple(skip.shape[1:4]) != out_sp:
             raise RuntimeError(f"The size of tensor a {out_sp} must match the size of tensor b "
                                f"{tuple(skip.shape[1:4])} (summation join, components.py:284)")
-        wp = k_pack_weights(weight, cin, cout, x.dtype, 0, transposed=True)
-        y = k_conv3(x, wp, cout, out_sp, 1, 1, bias=bias.detach().float() if bias is not None else None,
+        # tensor cores: 8 output-parity sub-convolutions of 1/2/4/8 taps over the input grid (one launch)
+        impl_id = conv_select_impl(x.shape, out_sp, cin, cout, x.dtype, 1, impl, x.data_ptr(), 0, 0)
+        wp = k_pack_weights(weight, cin, cout, x.dtype, 4 if impl_id == 2 else 0, transposed=True)
+        y = k_conv3(x, wp, cout, out_sp, 1, impl_id, bias=bias.detach().float() if bias is not None else None,
                     addend=_c(skip) if skip is not None else None)
         ctx.save_for_backward(x, weight)
         ctx.has_bias, ctx.has_skip, ctx.impl = bias is not None, skip is not None, impl
@@ -598,8 +600,10 @@ class ConvTranspose3x3Fn(torch.autograd.Function):
         cin, cout = weight.shape[0], weight.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wp = k_pack_weights(weight, cin, cout, dy.dtype, 1, transposed=True)
-            dx = k_conv3(dy, wp, cin, tuple(x.shape[1:4]), 2, 1)
+            in_sp = tuple(x.shape[1:4])
+            impl_id = conv_select_impl(dy.shape, in_sp, cout, cin, dy.dtype, 2, ctx.impl, dy.data_ptr(), 0, 0)
+            wp = k_pack_weights(weight, cin, cout, dy.dtype, 5 if impl_id == 2 else 1, transposed=True)
+            dx = k_conv3(dy, wp, cin, in_sp, 2, impl_id)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = k_wgrad(x, dy, 2, "simt", want_bias=ctx.has_bias)
         return dx, dw, db, (dy if ctx.has_skip else None), None
