@@ -48,6 +48,10 @@ struct WgArgs {
   int tiles_d, tiles_h, tiles_w;
   int64_t bricks;              // N * tiles_d * tiles_h * tiles_w
   int u_tiles, s_chunks, ksplit;
+  // transposed convolution (gather CONVT_B): the operand on the 2x grid (dY) is read through a stride-2 TMA map at
+  // parity (cls >> 2, cls >> 1 & 1, cls & 1); one launch per parity class, only the (kd, kh) groups in gmask are needed
+  int u_scale, s_scale, cls;
+  uint32_t gmask;
   int wt_fastest;              // block index order: 1 = work type fastest (bricks shared through L2), 0 = split fastest
   int64_t bricks_per_split;
   float* partial;              // [ksplit][worktype][128][PART_COLS]
@@ -83,6 +87,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   const int ut = wt / p.s_chunks;
   const int ngroups = role == 0 ? GROUPS0 : 9 - GROUPS0;
   const int g0 = role == 0 ? 0 : GROUPS0;
+  if (((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u) return;     // this role owns no needed tap group (whole CTA)
   const int64_t b_begin = (int64_t)ks * p.bricks_per_split;
   int64_t b_end = b_begin + p.bricks_per_split;
   if (b_end > p.bricks) b_end = p.bricks;
@@ -117,9 +122,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         tc::mbar_wait(&empty[st], ph ^ 1u);
         tc::mbar_arrive_expect_tx(&full[st], (uint32_t)(u_bytes + s_bytes_raw));
         uint8_t* dst = smem + (size_t)st * stage_bytes;
-        tc::tma_load_5d(dst, &map_u, &full[st], ut * 128, w0, h0, d0, n);
-        tc::tma_load_5d(dst + u_atom_bytes, &map_u, &full[st], ut * 128 + 64, w0, h0, d0, n);
-        tc::tma_load_5d(dst + u_bytes, &map_s, &full[st], sc * CS, w0 - 1, h0 - 1, d0 - 1, n);
+        const int us = p.u_scale, ss = p.s_scale;
+        const int upd = us > 1 ? (p.cls >> 2) : 0, uph = us > 1 ? ((p.cls >> 1) & 1) : 0, upw = us > 1 ? (p.cls & 1) : 0;
+        const int spd = ss > 1 ? (p.cls >> 2) : 0, sph = ss > 1 ? ((p.cls >> 1) & 1) : 0, spw = ss > 1 ? (p.cls & 1) : 0;
+        tc::tma_load_5d(dst, &map_u, &full[st], ut * 128, us * w0 + upw, us * h0 + uph, us * d0 + upd, n);
+        tc::tma_load_5d(dst + u_atom_bytes, &map_u, &full[st], ut * 128 + 64, us * w0 + upw, us * h0 + uph, us * d0 + upd, n);
+        tc::tma_load_5d(dst + u_bytes, &map_s, &full[st], sc * CS, ss * (w0 - 1) + spw, ss * (h0 - 1) + sph,
+                        ss * (d0 - 1) + spd, n);
       }
     }
   } else if (warp == 1) {
@@ -156,7 +165,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
             const uint64_t db = db_z + (uint64_t)((hp * 2 * HL_W * 2 * CS) >> 4);
 #pragma unroll
             for (int g = 0; g < GROUPS0; ++g) {
-              if (g < ngroups) tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
+              if (g < ngroups && ((p.gmask >> (g0 + g)) & 1u))
+                tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
             }
             acc = 1u;
           }
@@ -194,13 +204,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
 
 // dw[co][ci][kd][kh][kw] (+)= sum over splits of the partial accumulators, fixed order
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
-                                       int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate) {
+                                       int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls) {
   const int64_t total = (int64_t)Cout * Cin * 27;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int tap = (int)(i % 27);
     const int ci = (int)((i / 27) % Cin);
     const int co = (int)(i / (27 * (int64_t)Cin));
     int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    if (cls >= 0) {
+      // transposed conv: kernel tap k belongs to dY parity (k != 1) per axis and window tap (k == 0 ? 0 : 1)
+      if ((((kd != 1) << 2) | ((kh != 1) << 1) | (kw != 1)) != cls) continue;
+      kd = kd == 0 ? 0 : 1; kh = kh == 0 ? 0 : 1; kw = kw == 0 ? 0 : 1;
+    }
     int cu, cs;
     if (u_is_x) { cu = ci; cs = co; kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
     else { cu = co; cs = ci; }
@@ -223,7 +238,10 @@ struct WgPlan {
 };
 
 bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
-  if (q->dtype != MEDNET_BF16 || q->gather != MEDNET_GATHER_CONV3) return false;
+  if (q->dtype != MEDNET_BF16) return false;
+  const bool convt = q->gather == MEDNET_GATHER_CONVT_B;      // a = x on the small grid, b = dY on the 2x grid
+  if (q->gather != MEDNET_GATHER_CONV3 && !convt) return false;
+  if (convt && (q->Db != 2 * q->Da || q->Hb != 2 * q->Ha || q->Wb != 2 * q->Wa)) return false;
   if (!mednet_device_has_tcgen05()) return false;
   if (((uintptr_t)q->a | (uintptr_t)q->b) & 15) return false;
   WgPlan pl;
@@ -235,6 +253,9 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   if (CU % 8 != 0 || CSn % 8 != 0) return false;
   WgArgs& a = pl.a;
   a.N = q->N; a.D = q->Da; a.H = q->Ha; a.W = q->Wa; a.CU = CU; a.CSn = CSn;
+  a.u_scale = (convt && pl.u_is_x) ? 2 : 1;                   // "u_is_x": U is operand b
+  a.s_scale = (convt && !pl.u_is_x) ? 2 : 1;
+  a.cls = 0; a.gmask = 0x1ffu;
   a.TD = q->Da >= 2 ? 2 : 1;
   a.tiles_d = ceil_div(a.D, a.TD); a.tiles_h = ceil_div(a.H, BR_H); a.tiles_w = ceil_div(a.W, BR_W);
   a.bricks = (int64_t)a.N * a.tiles_d * a.tiles_h * a.tiles_w;
@@ -282,12 +303,15 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   const void* u_ptr = pl.u_is_x ? q->b : q->a;
   const void* s_ptr = pl.u_is_x ? q->a : q->b;
   CUtensorMap map_u, map_s;
+  const bool convt = q->gather == MEDNET_GATHER_CONVT_B;
   {
     const cuuint64_t C = (cuuint64_t)a.CU;
-    cuuint64_t dims[5] = {C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.N};
-    cuuint64_t strides[4] = {C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2, (cuuint64_t)a.D * a.H * a.W * C * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)BR_W, (cuuint32_t)BR_H, (cuuint32_t)a.TD, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t GD = pl.u_is_x ? q->Db : q->Da, GH = pl.u_is_x ? q->Hb : q->Ha, GW = pl.u_is_x ? q->Wb : q->Wa;
+    const cuuint32_t es = (cuuint32_t)a.u_scale;
+    cuuint64_t dims[5] = {C, GW, GH, GD, (cuuint64_t)a.N};
+    cuuint64_t strides[4] = {C * 2, GW * C * 2, GH * GW * C * 2, GD * GH * GW * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)BR_W * es, (cuuint32_t)BR_H * es, (cuuint32_t)a.TD * es, 1};
+    cuuint32_t estr[5] = {1, es, es, es, 1};
     if (enc(&map_u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(u_ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -295,10 +319,12 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   }
   {
     const cuuint64_t C = (cuuint64_t)a.CSn;
-    cuuint64_t dims[5] = {C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.N};
-    cuuint64_t strides[4] = {C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2, (cuuint64_t)a.D * a.H * a.W * C * 2};
-    cuuint32_t box[5] = {(cuuint32_t)CS, (cuuint32_t)HL_W, (cuuint32_t)HL_H, (cuuint32_t)(a.TD + 2), 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t GD = pl.u_is_x ? q->Da : q->Db, GH = pl.u_is_x ? q->Ha : q->Hb, GW = pl.u_is_x ? q->Wa : q->Wb;
+    const cuuint32_t es = (cuuint32_t)a.s_scale;
+    cuuint64_t dims[5] = {C, GW, GH, GD, (cuuint64_t)a.N};
+    cuuint64_t strides[4] = {C * 2, GW * C * 2, GH * GW * C * 2, GD * GH * GW * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)CS, (cuuint32_t)HL_W * es, (cuuint32_t)HL_H * es, (cuuint32_t)(a.TD + 2) * es, 1};
+    cuuint32_t estr[5] = {1, es, es, es, 1};
     if (enc(&map_s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s_ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -314,14 +340,37 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
       configured = pl.smem;
     }
   }
-  wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
-  MEDNET_LAUNCH_CHECK();
   const int64_t total = (int64_t)q->Ca * q->Cb * 27;
-  wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
-                                                               a.ksplit, a.u_tiles * a.s_chunks * 2, q->accumulate);
-  MEDNET_LAUNCH_CHECK();
+  const int worktypes = a.u_tiles * a.s_chunks * 2;
+  if (!convt) {
+    wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
+    MEDNET_LAUNCH_CHECK();
+    wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
+                                                                 a.ksplit, worktypes, q->accumulate, -1);
+    MEDNET_LAUNCH_CHECK();
+  } else {
+    // one pass per parity class of dY: window taps {1} (parity 0) / {0, 1} (parity 1) per axis -> at most 4 of the 9
+    // (kd, kh) groups (mirrored when U is the strided operand); the reduce pass of each class writes only its taps
+    for (int cls = 0; cls < 8; ++cls) {
+      uint32_t gm = 0;
+      for (int kd = 0; kd < 2; ++kd)
+        for (int kh = 0; kh < 2; ++kh) {
+          if ((kd == 0 && !(cls & 4)) || (kh == 0 && !(cls & 2))) continue;     // window tap 0 exists for parity 1 only
+          const int gd = pl.u_is_x ? 2 - kd : kd, gh = pl.u_is_x ? 2 - kh : kh;
+          gm |= 1u << (gd * 3 + gh);
+        }
+      a.cls = cls; a.gmask = gm;
+      wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
+      MEDNET_LAUNCH_CHECK();
+      wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
+                                                                   a.ksplit, worktypes, q->accumulate, cls);
+      MEDNET_LAUNCH_CHECK();
+    }
+  }
   if (q->dbias != nullptr) {
     void* cpart = (char*)workspace + pl.partial_bytes;
+    if (convt)    // bias gradient = column sums of the output-gradient operand (b for the transposed conv)
+      return colsum_bias(q->b, q->dtype, (int64_t)q->N * q->Db * q->Hb * q->Wb, q->Cb, q->dbias, q->accumulate, cpart, st);
     return colsum_bias(q->a, q->dtype, (int64_t)q->N * q->Da * q->Ha * q->Wa, q->Ca, q->dbias, q->accumulate, cpart, st);
   }
   return MEDNET_OK;

@@ -605,7 +605,7 @@ class ConvTranspose3x3Fn(torch.autograd.Function):
             wp = k_pack_weights(weight, cin, cout, dy.dtype, 5 if impl_id == 2 else 1, transposed=True)
             dx = k_conv3(dy, wp, cin, in_sp, 2, impl_id)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = k_wgrad(x, dy, 2, "simt", want_bias=ctx.has_bias)
+            dw, db = k_wgrad(x, dy, 2, "simt" if ctx.impl == "simt" else "auto", want_bias=ctx.has_bias)
         return dx, dw, db, (dy if ctx.has_skip else None), None
 
 
