@@ -349,9 +349,16 @@ def main():
     tc_flops = sum(f for f, _, _ in conv_events)
     tc_ms = sum(a.elapsed_time(b) for _, a, b in conv_events)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    if args.workload == "cfg3":
+        try:                                  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
     roofline = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 fprop+dgrad)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None, "peak_source": peak_src, "launches_timed": len(conv_events),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_timed": len(conv_events),
                 "share_of_step": tc_ms / ms if ms else None}
     line = {"metric": "UNet3D train voxels/s", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
