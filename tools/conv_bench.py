@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--wgrad-impl", default="auto")
     ap.add_argument("--dual-issue", type=int, default=1)
     ap.add_argument("--wt-fastest", type=int, default=1)
+    ap.add_argument("--pair-planes", type=int, default=1)
     ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
@@ -48,6 +49,7 @@ def main():
     from mednet_b200._abi import check, lib
     check(lib().mednet_tcgen05_set_option(b"dual_issue", a.dual_issue), "set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_wt_fastest", a.wt_fastest), "set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_pair_planes", a.pair_planes), "set_option")
     layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
     for cin, cout, div in layers:
         s = a.edge // div
@@ -70,7 +72,7 @@ def main():
         if "wgrad" in a.passes:
             ms = timed(lambda: ops.k_wgrad(dy, x, 0, a.wgrad_impl), a.reps)
             print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9,
-                                  wt_fastest=a.wt_fastest)))
+                                  wt_fastest=a.wt_fastest, pair_planes=a.pair_planes)))
         del x, dy
 
 

@@ -30,6 +30,7 @@ namespace mednet {
 
 namespace {
 
+int g_pair_planes = 1;        // mednet_tcgen05_set_option("wgrad_pair_planes", 0|1)
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
 
 constexpr int WG_THREADS = 192;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue
@@ -52,13 +53,16 @@ struct WgArgs {
   // parity (cls >> 2, cls >> 1 & 1, cls & 1); one launch per parity class, only the (kd, kh) groups in gmask are needed
   int u_scale, s_scale, cls;
   uint32_t gmask;
+  int ut_base;                 // first U tile of this launch (the paired tail tile is launched separately)
+  int pair_ok;                 // 1: U tiles with <= 64 real channels use the paired-plane mode (see kernel)
   int wt_fastest;              // block index order: 1 = work type fastest (bricks shared through L2), 0 = split fastest
   int64_t bricks_per_split;
   float* partial;              // [ksplit][worktype][128][PART_COLS]
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s, const WgArgs p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
+                const __grid_constant__ CUtensorMap map_u2, const WgArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int u_atom_bytes = p.TD * 128 * 128;                       // one 64-channel atom of the brick
@@ -84,13 +88,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   const int wt0 = wt;          // partial buffer layout [ks][work type] whatever the launch order
   const int role = wt & 1; wt >>= 1;
   const int sc = wt % p.s_chunks;
-  const int ut = wt / p.s_chunks;
-  const int ngroups = role == 0 ? GROUPS0 : 9 - GROUPS0;
-  const int g0 = role == 0 ? 0 : GROUPS0;
-  if (((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u) return;     // this role owns no needed tap group (whole CTA)
-  const int64_t b_begin = (int64_t)ks * p.bricks_per_split;
-  int64_t b_end = b_begin + p.bricks_per_split;
-  if (b_end > p.bricks) b_end = p.bricks;
+  const int ut = wt / p.s_chunks + p.ut_base;
+  // PAIRED-PLANE mode for a U tile with <= 64 real channels (64-channel layers; the 64-channel tail of a 192-channel
+  // U): instead of leaving accumulator rows 64..127 empty, the second 64-row atom of A points at the SAME channels one
+  // d-plane further (leading-dimension offset = one 16 KB plane of a (TD + 1)-plane brick).  With the S window at
+  // (gd, gh), rows 0..63 accumulate tap (gd, gh, .) and rows 64..127 tap (gd - 1, gh, .): S windows gd = 1 (role 0) and
+  // gd = 2 (role 1) cover all three kd taps with 3 MMAs per K step and CTA instead of 5 / 4.  The second half sums over
+  // planes d0 + 1 .. d0 + TD, so the brick grid gets one extra layer at d0 = -TD (everything else there is zero fill).
+  const bool paired = p.pair_ok && (p.CU - ut * 128) <= 64;
+  const int ngroups = paired ? 3 : (role == 0 ? GROUPS0 : 9 - GROUPS0);
+  const int g0 = paired ? 0 : (role == 0 ? 0 : GROUPS0);
+  if (!paired && ((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u) return;   // this role owns no needed tap group (whole CTA)
+  const int tiles_d = p.tiles_d + (paired ? 1 : 0);
+  const int64_t bricks = (int64_t)p.N * tiles_d * p.tiles_h * p.tiles_w;
+  const int64_t per_split = (bricks + p.ksplit - 1) / p.ksplit;
+  const int64_t b_begin = (int64_t)ks * per_split;
+  int64_t b_end = b_begin + per_split;
+  if (b_end > bricks) b_end = bricks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -98,6 +112,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
     tc::fence_barrier_init();
     tc::tma_prefetch_desc(&map_u);
     tc::tma_prefetch_desc(&map_s);
+    tc::tma_prefetch_desc(&map_u2);
   }
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, 512u);
@@ -117,11 +132,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         int64_t t = b;
         const int w0 = (int)(t % p.tiles_w) * BR_W; t /= p.tiles_w;
         const int h0 = (int)(t % p.tiles_h) * BR_H; t /= p.tiles_h;
-        const int d0 = (int)(t % p.tiles_d) * p.TD;
-        const int n = (int)(t / p.tiles_d);
+        const int d0 = (int)(t % tiles_d) * p.TD - (paired ? p.TD : 0);
+        const int n = (int)(t / tiles_d);
         tc::mbar_wait(&empty[st], ph ^ 1u);
-        tc::mbar_arrive_expect_tx(&full[st], (uint32_t)(u_bytes + s_bytes_raw));
         uint8_t* dst = smem + (size_t)st * stage_bytes;
+        if (paired) {
+          tc::mbar_arrive_expect_tx(&full[st], (uint32_t)((p.TD + 1) * 128 * 128 + s_bytes_raw));
+          tc::tma_load_5d(dst, &map_u2, &full[st], ut * 128, w0, h0, d0, n);
+          tc::tma_load_5d(dst + u_bytes, &map_s, &full[st], sc * CS, w0 - 1, h0 - 1, d0 - 1, n);
+          continue;
+        }
+        tc::mbar_arrive_expect_tx(&full[st], (uint32_t)(u_bytes + s_bytes_raw));
         const int us = p.u_scale, ss = p.s_scale;
         const int upd = us > 1 ? (p.cls >> 2) : 0, uph = us > 1 ? ((p.cls >> 1) & 1) : 0, upw = us > 1 ? (p.cls & 1) : 0;
         const int spd = ss > 1 ? (p.cls >> 2) : 0, sph = ss > 1 ? ((p.cls >> 1) & 1) : 0, spw = ss > 1 ? (p.cls & 1) : 0;
@@ -140,7 +161,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
 #pragma unroll
       for (int g = 0; g < GROUPS0; ++g) {
         const int gg = g0 + (g < ngroups ? g : 0);
-        const int gd = gg / 3, gh = gg - gd * 3;
+        const int gd = paired ? 1 + role : gg / 3, gh = paired ? gg : gg - gd * 3;
         goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W) * (2 * CS)) >> 4;
       }
       const uint32_t s_base = tc::smem_u32(smem);
@@ -151,7 +172,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         tc::tc_fence_after();
         const uint32_t u_addr = s_base + st * (uint32_t)stage_bytes;
         // A: MN-major, 128-byte rows, atoms u_atom_bytes apart, 8-row groups 1024 B apart
-        const uint64_t da0 = tc::make_smem_desc(u_addr, (uint32_t)u_atom_bytes, 1024u, 0, tc::SWZ_128B);
+        const uint64_t da0 = tc::make_smem_desc(u_addr, paired ? 128u * 128u : (uint32_t)u_atom_bytes, 1024u, 0, tc::SWZ_128B);
         // B: MN-major, 64-byte rows, three chained windows one row (64 B) apart, 8-row groups = next halo row
         const uint64_t db0 = tc::make_smem_desc(u_addr + (uint32_t)u_bytes, (uint32_t)(2 * CS), (uint32_t)(HL_W * 2 * CS), 0,
                                                 tc::SWZ_64B);
@@ -165,7 +186,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
             const uint64_t db = db_z + (uint64_t)((hp * 2 * HL_W * 2 * CS) >> 4);
 #pragma unroll
             for (int g = 0; g < GROUPS0; ++g) {
-              if (g < ngroups && ((p.gmask >> (g0 + g)) & 1u))
+              if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u)))
                 tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
             }
             acc = 1u;
@@ -204,7 +225,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
 
 // dw[co][ci][kd][kh][kw] (+)= sum over splits of the partial accumulators, fixed order
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
-                                       int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls) {
+                                       int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
+                                       int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset) {
+  // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
+  // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int tap = (int)(i % 27);
@@ -219,22 +243,36 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     int cu, cs;
     if (u_is_x) { cu = ci; cs = co; kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
     else { cu = co; cs = ci; }
-    const int g = kd * 3 + kh;
-    const int role = g >= GROUPS0 ? 1 : 0;
-    const int gl = g - role * GROUPS0;
-    const int wt = ((cu >> 7) * s_chunks + cs / CS) * 2 + role;
-    const float* src = partial + ((size_t)wt * 128 + (cu & 127)) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
+    int role, gl, row = cu & 127;
+    if (pair_ok && (CU - (cu >> 7) * 128) <= 64) {
+      // paired-plane tile: role 0 (S window gd = 1) holds tap kd = 1 in rows 0..63 and kd = 0 in rows 64..127,
+      // role 1 (gd = 2) holds kd = 2 in rows 0..63; the (kd, kh) group index inside the CTA is kh
+      role = kd == 2 ? 1 : 0;
+      gl = kh;
+      row = (cu & 63) + (kd == 0 ? 64 : 0);
+    } else {
+      const int g = kd * 3 + kh;
+      role = g >= GROUPS0 ? 1 : 0;
+      gl = g - role * GROUPS0;
+    }
+    const int tile = cu >> 7;
+    const bool s1 = tile >= seg1_tile;
+    const int wt = ((tile - (s1 ? seg1_tile : 0)) * s_chunks + cs / CS) * 2 + role;
+    const int nk = s1 ? ksplit1 : ksplit, nw = s1 ? worktypes1 : worktypes;
+    const float* src = partial + (s1 ? seg1_offset : 0) + ((size_t)wt * 128 + row) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
     float acc = 0.f;
-    for (int k = 0; k < ksplit; ++k) acc += src[(size_t)k * worktypes * 128 * PART_COLS];
+    for (int k = 0; k < nk; ++k) acc += src[(size_t)k * nw * 128 * PART_COLS];
     dw[i] = accumulate ? dw[i] + acc : acc;
   }
 }
 
+struct WgSeg { int ut_base, u_tiles, ksplit, grid; size_t offset_floats; };
 struct WgPlan {
   WgArgs a;
   int u_is_x;
   size_t partial_bytes, smem;
-  int grid;
+  int nseg;
+  WgSeg seg[2];              // [0] full 128-channel U tiles, [1] the paired 64-channel tail tile (own split factor)
 };
 
 bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
@@ -256,19 +294,36 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   a.u_scale = (convt && pl.u_is_x) ? 2 : 1;                   // "u_is_x": U is operand b
   a.s_scale = (convt && !pl.u_is_x) ? 2 : 1;
   a.cls = 0; a.gmask = 0x1ffu;
+  a.pair_ok = (!convt && g_pair_planes) ? 1 : 0;
   a.TD = q->Da >= 2 ? 2 : 1;
   a.tiles_d = ceil_div(a.D, a.TD); a.tiles_h = ceil_div(a.H, BR_H); a.tiles_w = ceil_div(a.W, BR_W);
   a.bricks = (int64_t)a.N * a.tiles_d * a.tiles_h * a.tiles_w;
-  a.u_tiles = ceil_div(CU, 128); a.s_chunks = ceil_div(CSn, CS);
-  const int worktypes = a.u_tiles * a.s_chunks * 2;
+  a.s_chunks = ceil_div(CSn, CS);
+  const int tiles_all = ceil_div(CU, 128);
+  const bool tail_paired = a.pair_ok && (CU - (tiles_all - 1) * 128) <= 64;
   const int sms = sm_count_cached();
-  int64_t ksplit = (2 * sms + worktypes - 1) / worktypes;       // ~2 CTAs per SM in total: bounded tail
-  if (ksplit > a.bricks) ksplit = a.bricks;
-  if (ksplit < 1) ksplit = 1;
-  a.bricks_per_split = ceil_div64(a.bricks, ksplit);
-  a.ksplit = (int)ceil_div64(a.bricks, a.bricks_per_split);
-  pl.grid = worktypes * a.ksplit;
-  pl.partial_bytes = align_up((size_t)pl.grid * 128 * PART_COLS * sizeof(float), 256);
+  pl.nseg = 0;
+  size_t off = 0;
+  auto add_seg = [&](int ut_base, int u_tiles, bool paired) {
+    WgSeg& sg = pl.seg[pl.nseg++];
+    sg.ut_base = ut_base; sg.u_tiles = u_tiles;
+    const int worktypes = u_tiles * a.s_chunks * 2;
+    const int64_t bricks = (int64_t)a.N * (a.tiles_d + (paired ? 1 : 0)) * a.tiles_h * a.tiles_w;
+    int64_t ksplit = (2 * sms + worktypes - 1) / worktypes;     // ~2 CTAs per SM per launch: bounded tail
+    if (ksplit > bricks) ksplit = bricks;
+    if (ksplit < 1) ksplit = 1;
+    sg.ksplit = (int)ceil_div64(bricks, ceil_div64(bricks, ksplit));
+    sg.grid = worktypes * sg.ksplit;
+    sg.offset_floats = off;
+    off += (size_t)sg.grid * 128 * PART_COLS;
+  };
+  if (tail_paired) {
+    if (tiles_all > 1) add_seg(0, tiles_all - 1, false);
+    add_seg(tiles_all - 1, 1, true);
+  } else {
+    add_seg(0, tiles_all, false);
+  }
+  pl.partial_bytes = align_up(off * sizeof(float), 256);
   const size_t u_bytes = (size_t)2 * a.TD * 128 * 128;
   const size_t s_bytes = align_up((size_t)(a.TD + 2) * HL_H * HL_W * 2 * CS, 1024);
   pl.smem = 1024 + STAGES * (u_bytes + s_bytes) + 128;
@@ -280,6 +335,7 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
 }  // namespace
 
 void tc_wgrad_set_wt_fastest(int v) { g_wt_fastest = v ? 1 : 0; }
+void tc_wgrad_set_pair_planes(int v) { g_pair_planes = v ? 1 : 0; }
 
 bool tc_wgrad_supported(const mednet_wgrad_params* q) {
   WgPlan pl;
@@ -298,7 +354,6 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return MEDNET_ENODRIVER;
   WgArgs& a = pl.a;
-  a.partial = (float*)workspace;
   a.wt_fastest = g_wt_fastest;
   const void* u_ptr = pl.u_is_x ? q->b : q->a;
   const void* s_ptr = pl.u_is_x ? q->a : q->b;
@@ -313,6 +368,18 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     cuuint32_t box[5] = {64, (cuuint32_t)BR_W * es, (cuuint32_t)BR_H * es, (cuuint32_t)a.TD * es, 1};
     cuuint32_t estr[5] = {1, es, es, es, 1};
     if (enc(&map_u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(u_ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MEDNET_EUNSUPPORTED;
+  }
+  CUtensorMap map_u2 = map_u;
+  if (a.pair_ok) {       // paired-plane bricks: one 64-channel atom, TD + 1 planes
+    const cuuint64_t C = (cuuint64_t)a.CU;
+    cuuint64_t dims[5] = {C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.N};
+    cuuint64_t strides[4] = {C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2, (cuuint64_t)a.D * a.H * a.W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)BR_W, (cuuint32_t)BR_H, (cuuint32_t)(a.TD + 1), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&map_u2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(u_ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MEDNET_EUNSUPPORTED;
@@ -341,13 +408,32 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     }
   }
   const int64_t total = (int64_t)q->Ca * q->Cb * 27;
-  const int worktypes = a.u_tiles * a.s_chunks * 2;
+  const WgSeg& s0 = pl.seg[0];
+  const WgSeg& s1 = pl.seg[pl.nseg - 1];
+  // reduce-kernel view: tiles >= seg1_tile live in the second segment (none when there is a single segment)
+  const int seg1_tile = pl.nseg == 2 ? s1.ut_base : (1 << 20);
+  auto launch_all = [&]() -> int {
+    for (int i = 0; i < pl.nseg; ++i) {
+      const WgSeg& sg = pl.seg[i];
+      a.ut_base = sg.ut_base; a.u_tiles = sg.u_tiles; a.ksplit = sg.ksplit;
+      a.partial = (float*)workspace + sg.offset_floats;
+      wgrad_tc_kernel<<<(unsigned)sg.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, map_u2, a);
+      MEDNET_LAUNCH_CHECK();
+    }
+    return MEDNET_OK;
+  };
+  auto reduce = [&](int cls) -> int {
+    wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+        (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * 2,
+        q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats);
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  };
   if (!convt) {
-    wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
-    MEDNET_LAUNCH_CHECK();
-    wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
-                                                                 a.ksplit, worktypes, q->accumulate, -1);
-    MEDNET_LAUNCH_CHECK();
+    int r = launch_all();
+    if (r != MEDNET_OK) return r;
+    r = reduce(-1);
+    if (r != MEDNET_OK) return r;
   } else {
     // one pass per parity class of dY: window taps {1} (parity 0) / {0, 1} (parity 1) per axis -> at most 4 of the 9
     // (kd, kh) groups (mirrored when U is the strided operand); the reduce pass of each class writes only its taps
@@ -360,11 +446,10 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
           gm |= 1u << (gd * 3 + gh);
         }
       a.cls = cls; a.gmask = gm;
-      wgrad_tc_kernel<<<(unsigned)pl.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, a);
-      MEDNET_LAUNCH_CHECK();
-      wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.partial, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks,
-                                                                   a.ksplit, worktypes, q->accumulate, cls);
-      MEDNET_LAUNCH_CHECK();
+      int r = launch_all();
+      if (r != MEDNET_OK) return r;
+      r = reduce(cls);
+      if (r != MEDNET_OK) return r;
     }
   }
   if (q->dbias != nullptr) {
