@@ -87,6 +87,14 @@ typedef struct {
 } mednet_layout_params;
 int mednet_layout_convert(const mednet_layout_params* p, mednet_stream_t stream);
 
+/* Channel padding / extraction of NDHWC rows: dst[r][c] = c < Cs ? src[r][c] : 0 (Cd >= Cs) or dst[r][c] = src[r][c]
+ * for c < Cd (Cd < Cs).  Used to run the in_channels = 1 first layer (mm/segmentation.py:30-31) on the tensor cores:
+ * the image is zero-padded to 16 channels once, the input gradient is cut back to the real channels. */
+typedef struct {
+  const void* src; void* dst; int64_t rows; int32_t Cs, Cd, dtype;
+} mednet_chpad_params;
+int mednet_channel_pad(const mednet_chpad_params* p, mednet_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3x3x3 convolution, stride 1, zero padding 1 (also hosts ConvTranspose3d through `gather`).
  * ref: mm/unet/components.py:8-9 (nn.Conv3d via create_conv :41-44); transposed: :259-264.

@@ -260,9 +260,35 @@ __global__ void upcat_bwd_low_kernel(const T* __restrict__ dout, T* __restrict__
   }
 }
 
+// dst[r][0..Cd) from src[r][0..Cs): zero fill past Cs (pad) or truncation (extract); one thread per destination row
+template <typename T>
+__global__ void channel_pad_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int Cs, int Cd) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    if (Cd == 16 && sizeof(T) == 2) {                       // the first-layer case: one 32-byte row per thread
+      union { U32B v; T t[16]; } u;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) u.t[c] = c < Cs ? src[r * Cs + c] : from_f32<T>(0.f);
+      *reinterpret_cast<U32B*>(dst + r * 16) = u.v;
+    } else {
+      for (int c = 0; c < Cd; ++c) dst[r * Cd + c] = c < Cs ? src[r * Cs + c] : from_f32<T>(0.f);
+    }
+  }
+}
+
 }  // namespace mednet
 
 using namespace mednet;
+
+extern "C" int mednet_channel_pad(const mednet_chpad_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->src && p->dst && p->rows > 0 && p->Cs > 0 && p->Cd > 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  if (p->dtype == MEDNET_F32)
+    channel_pad_kernel<float><<<grid_for(p->rows, 256), 256, 0, stream>>>((const float*)p->src, (float*)p->dst, p->rows, p->Cs, p->Cd);
+  else
+    channel_pad_kernel<bf16><<<grid_for(p->rows, 256), 256, 0, stream>>>((const bf16*)p->src, (bf16*)p->dst, p->rows, p->Cs, p->Cd);
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
 
 extern "C" int mednet_layout_convert(const mednet_layout_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->src && p->dst && p->N > 0 && p->C > 0 && p->S > 0, MEDNET_EINVAL);
