@@ -156,7 +156,11 @@ def k_channel_pad(x, c_dst):
     return out
 
 
-FIRST_LAYER_PAD = 16      # in_channels < 16 (the 1-channel image): pad to 16 channels and use the tensor-core kernels
+# in_channels < 16 (the 1-channel image) can be zero-padded to 16 channels to run the first layer on the tensor-core
+# kernels (set to 16).  Measured on cfg-3 (profiles/r01j_first_layer_pad.txt): K = 16 leaves 2 MMAs per tap and issuer,
+# so the launches are latency-bound (2.3 ms each for fprop / dgrad, 1.9 ms wgrad) and the step is 1.1 ms SLOWER than with
+# the register-tiled CUDA-core stencil kernels (1.5 / 1.7 / 1.9 ms) -> off by default.
+FIRST_LAYER_PAD = 0
 
 
 def conv_select_impl(x_shape, out_sp, K, Nout, dtype, gather, impl, x_ptr=0, w_ptr=0, y_ptr=0):
