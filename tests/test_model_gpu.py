@@ -192,3 +192,32 @@ def test_sliding_window_predictor_matches_reference_loop():
     a = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=0, world=2)(vol, combine=False)
     b = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=1, world=2)(vol, combine=False)
     assert np.array_equal(torch.maximum(a, b).cpu().numpy(), got)
+
+
+def test_async_weight_gradients_match_the_synchronous_path():
+    """FusedAdam marks the conv weights' .grad (views of its flat buffer) for asynchronous accumulation: their wgrad
+    kernels run on a side stream and write straight into the buffer (ops.wgrad_async).  Same kernels, same order of
+    summation -> the flat gradient must be bit-identical to the synchronous autograd path, also when gradients are
+    accumulated over two backward passes."""
+    from mednet_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    x = torch.randn(2, 1, 16, 32, 16, device=DEV)
+    y = torch.randint(0, 3, (2, 16, 32, 16), device=DEV)
+    grads = []
+    for async_wgrad in (False, True):
+        torch.manual_seed(1)
+        net = UNet3D(1, 3, False, f_maps=[16, 32, 64]).to(DEV)
+        opt = FusedAdam(net.parameters(), lr=1e-3, async_wgrad=async_wgrad)
+        opt.zero_grad()
+        marked = sum(bool(getattr(p, "_mednet_async_grad", False)) for p in net.parameters())
+        assert (marked > 0) == async_wgrad
+        for _ in range(2):                                   # accumulation over two backward passes
+            DiceLoss()(net(x), y).backward()
+        opt.sync_gradients()
+        torch.cuda.synchronize()
+        grads.append(opt.flat_grad.clone())
+        opt.step()
+        opt.zero_grad()
+        assert float(opt.flat_grad.abs().sum()) == 0.0
+    assert torch.equal(grads[0], grads[1])
+    assert float(grads[0].abs().sum()) > 0

@@ -236,6 +236,79 @@ def k_wgrad(a, b, gather, impl="auto", want_bias=False):
     return dw, dbias
 
 
+# =============================================================================================
+# asynchronous weight gradients
+# =============================================================================================
+# The weight gradient of a convolution depends only on (x, dpre) and is consumed only by the optimiser, while everything
+# else in backward is a serial chain (dgrad -> GroupNorm backward -> ...).  When a parameter's .grad lives in a buffer whose
+# owner promises to call sync_async_wgrad() before reading it (FusedAdam's flat gradient buffer does), its wgrad is enqueued
+# on a SIDE stream and accumulated straight into that buffer: the tensor-core wgrad kernels then overlap the memory-bound
+# GroupNorm / pool / join backward kernels of the following layers instead of running between them.
+_side_streams = {}
+_async_pending = False
+async_grad_listener = None      # callable(param): told when a parameter's gradient has been ENQUEUED on the side stream
+                                # (the data-parallel reducer counts its bucket down and launches the all-reduce behind it)
+
+
+def side_stream(device=None):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]
+
+
+def mark_async_grad(param, enabled=True):
+    """Owner of param.grad promises to call sync_async_wgrad() before reading or overwriting it."""
+    param._mednet_async_grad = bool(enabled)
+
+
+def sync_async_wgrad():
+    """Make the current stream wait for every weight gradient enqueued on the side stream."""
+    global _async_pending
+    if _async_pending:
+        torch.cuda.current_stream().wait_stream(side_stream())
+        _async_pending = False
+
+
+def _async_wgrad_ok(weight):
+    g = weight.grad
+    return (getattr(weight, "_mednet_async_grad", False) and g is not None and g.dtype == torch.float32 and
+            g.is_contiguous() and g.is_cuda)
+
+
+def k_wgrad_into(a, b, gather, impl, dw, accumulate=True):
+    """Weight gradient accumulated (or written) straight into `dw` (fp32, PyTorch layout) on the CURRENT stream."""
+    _need_cuda(a, b, dw)
+    p = wgrad_params(a, b, gather, impl, dw, None)
+    p.accumulate = int(accumulate)
+    ws = _ws(lib().mednet_conv3d_wgrad_workspace_bytes(_abi.C.byref(p)), a.device)
+    timing = conv_events is not None
+    if timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_wgrad")
+    if timing:
+        e1.record()
+        n, d, h, w = a.shape[:4]
+        wgrad_events.append((2.0 * n * d * h * w * a.shape[-1] * b.shape[-1] * 27, e0, e1))
+    _count(2)
+
+
+def wgrad_async(a, b, gather, impl, weight):
+    """Enqueue dW += wgrad(a, b) into weight.grad on the side stream (see the section comment)."""
+    global _async_pending
+    main, side = torch.cuda.current_stream(), side_stream(a.device)
+    side.wait_stream(main)                       # a / b (dpre, x) were produced on the main stream
+    with torch.cuda.stream(side):
+        k_wgrad_into(a, b, gather, impl, weight.grad, accumulate=True)
+    a.record_stream(side)                        # the caching allocator must not recycle them before the side stream is done
+    b.record_stream(side)
+    _async_pending = True
+    if async_grad_listener is not None:
+        async_grad_listener(weight)
+
+
 def k_conv1_fwd(x, w2d, bias):
     _need_cuda(x, w2d, bias)
     n, sp, cin = x.shape[0], tuple(x.shape[1:-1]), x.shape[-1]
@@ -582,6 +655,7 @@ class Conv3x3Fn(torch.autograd.Function):
         y = k_conv3(x, wp, cout, sp, 0, impl_id, bias=bias.detach().float() if bias is not None else None,
                     addend=add, act=act)
         bwd_act = 0 if defer_act else act
+        ctx.weight_ref = weight                      # the Parameter itself (its .grad buffer may be written asynchronously)
         ctx.save_for_backward(x, weight_eff.detach() if cin != ctx.cin_real else weight, y if bwd_act else None)
         ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = bwd_act, impl, bias is not None, addend is not None
         return y
@@ -601,9 +675,13 @@ class Conv3x3Fn(torch.autograd.Function):
             if cin != ctx.cin_real:
                 dx = k_channel_pad(dx, ctx.cin_real)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = k_wgrad(dpre, x, 0, "simt" if ctx.impl == "simt" else "auto", want_bias=ctx.has_bias)
-            if cin != ctx.cin_real:
-                dw = dw[:, :ctx.cin_real].contiguous()
+            wimpl = "simt" if ctx.impl == "simt" else "auto"
+            if not ctx.has_bias and cin == ctx.cin_real and _async_wgrad_ok(ctx.weight_ref):
+                wgrad_async(dpre, x, 0, wimpl, ctx.weight_ref)       # overlaps the rest of backward; dw stays None
+            else:
+                dw, db = k_wgrad(dpre, x, 0, wimpl, want_bias=ctx.has_bias)
+                if cin != ctx.cin_real:
+                    dw = dw[:, :ctx.cin_real].contiguous()
         return dx, dw, db, (dpre if ctx.has_addend else None), None, None, None
 
 

@@ -12,7 +12,7 @@ from . import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, async_wgrad=True):
         if weight_decay != 0:
             raise NotImplementedError("the reference uses Adam without weight decay")
         params = [p for p in params if p.requires_grad]
@@ -21,6 +21,9 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat = self._flat_grad = self._m = self._v = None
         self._step = 0
         self.grad_scale = 1.0
+        # weight gradients are written into the flat buffer on a side stream, overlapped with the rest of backward;
+        # every reader of the buffer (step, zero_grad, the all-reduce) first joins that stream
+        self.async_wgrad = bool(async_wgrad) and torch.cuda.is_available()
 
     # -- flat storage ---------------------------------------------------------------------------
     def _materialize(self):
@@ -41,6 +44,8 @@ class FusedAdam(torch.optim.Optimizer):
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self._flat_grad[off:off + n].view_as(p)
+                if self.async_wgrad and p.dim() == 5:
+                    ops.mark_async_grad(p)            # conv weights: wgrad goes to a side stream (ops.wgrad_async)
                 self._offsets.append((off, n))
                 off += n
 
@@ -54,8 +59,13 @@ class FusedAdam(torch.optim.Optimizer):
         self._materialize()
         return [(p, o, n) for p, (o, n) in zip(self._params, self._offsets)]
 
+    def sync_gradients(self):
+        """Join the side stream: after this the .grad tensors are complete on the current stream."""
+        ops.sync_async_wgrad()
+
     def zero_grad(self, set_to_none=False):
         self._materialize()
+        ops.sync_async_wgrad()
         self._flat_grad.zero_()
         for p, (off, n) in zip(self._params, self._offsets):
             if p.grad is None or p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * off:
@@ -64,6 +74,7 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         self._materialize()
+        ops.sync_async_wgrad()
         # gradients written by autograd into fresh tensors (first backward) are folded into the flat buffer
         for p, (off, n) in zip(self._params, self._offsets):
             if p.grad is not None and p.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * off:

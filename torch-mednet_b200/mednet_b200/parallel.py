@@ -58,6 +58,13 @@ class BucketedAllReduce:
         self.handles = []
         self.launch_order = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p, _, _ in grad_slices]
+        # conv weight gradients enqueued on the side stream (ops.wgrad_async) never pass through autograd's accumulation,
+        # so they report here; the all-reduce of a bucket is then launched BEHIND the side stream
+        self._ops = None
+        if flat_grad.is_cuda:
+            from . import ops
+            self._ops = ops
+            ops.async_grad_listener = self._on_grad
 
     def _on_grad(self, param):
         b = self.bucket_of[id(param)]
@@ -70,7 +77,16 @@ class BucketedAllReduce:
         lo, hi = self.buckets[b][0], self.buckets[b][1]
         self.launch_order.append(b)
         if self.world > 1:
-            self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self._ops is not None:
+                # the bucket holds gradients written on the main stream (autograd) and on the side stream (async wgrad):
+                # issue the collective from the side stream after it has caught up with the main stream
+                side = self._ops.side_stream(self.flat.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    h = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self.handles.append(h)
+            else:
+                self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
         """Call after backward: flushes buckets whose parameters got no gradient, waits for the collectives
@@ -81,6 +97,8 @@ class BucketedAllReduce:
         for h in self.handles:
             h.wait()
         self.handles.clear()
+        if self._ops is not None:
+            self._ops.sync_async_wgrad()
         self.launch_order.clear()
         for bucket in self.buckets:
             bucket[2] = bucket[3]
@@ -89,6 +107,8 @@ class BucketedAllReduce:
     def remove(self):
         for h in self._hooks:
             h.remove()
+        if self._ops is not None and self._ops.async_grad_listener == self._on_grad:
+            self._ops.async_grad_listener = None
 
 
 def init_distributed(backend=None):
