@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--dual-issue", type=int, default=1)
     ap.add_argument("--wt-fastest", type=int, default=1)
     ap.add_argument("--pair-planes", type=int, default=1)
+    ap.add_argument("--d-fastest", type=int, default=1)
     ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
@@ -50,6 +51,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"dual_issue", a.dual_issue), "set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_wt_fastest", a.wt_fastest), "set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_pair_planes", a.pair_planes), "set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_d_fastest", a.d_fastest), "set_option")
     layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
     for cin, cout, div in layers:
         s = a.edge // div

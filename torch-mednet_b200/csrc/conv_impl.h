@@ -18,6 +18,7 @@ int tc_fprop(const mednet_conv3d_params* p, cudaStream_t st);
 bool tc_wgrad_supported(const mednet_wgrad_params* p);
 void tc_wgrad_set_wt_fastest(int v);
 void tc_wgrad_set_pair_planes(int v);
+void tc_wgrad_set_d_fastest(int v);
 size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params* p);
 int tc_wgrad(const mednet_wgrad_params* p, void* workspace, cudaStream_t st);
 }  // namespace mednet

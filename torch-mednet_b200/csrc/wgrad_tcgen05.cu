@@ -31,6 +31,7 @@ namespace mednet {
 namespace {
 
 int g_pair_planes = 1;        // mednet_tcgen05_set_option("wgrad_pair_planes", 0|1)
+int g_d_fastest = 1;          // mednet_tcgen05_set_option("wgrad_d_fastest", 0|1)
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
 
 constexpr int WG_THREADS = 192;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue
@@ -55,6 +56,7 @@ struct WgArgs {
   uint32_t gmask;
   int ut_base;                 // first U tile of this launch (the paired tail tile is launched separately)
   int pair_ok;                 // 1: U tiles with <= 64 real channels use the paired-plane mode (see kernel)
+  int d_fastest;               // brick order inside a CTA: 1 = d fastest (halo planes reused from L2)
   int wt_fastest;              // block index order: 1 = work type fastest (bricks shared through L2), 0 = split fastest
   int64_t bricks_per_split;
   float* partial;              // [ksplit][worktype][128][PART_COLS]
@@ -96,8 +98,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   // gd = 2 (role 1) cover all three kd taps with 3 MMAs per K step and CTA instead of 5 / 4.  The second half sums over
   // planes d0 + 1 .. d0 + TD, so the brick grid gets one extra layer at d0 = -TD (everything else there is zero fill).
   const bool paired = p.pair_ok && (p.CU - ut * 128) <= 64;
-  const int ngroups = paired ? 3 : (role == 0 ? GROUPS0 : 9 - GROUPS0);
-  const int g0 = paired ? 0 : (role == 0 ? 0 : GROUPS0);
+  // Unpaired tiles: role 0 holds tap groups 0..4, role 1 groups 4..8 (5 accumulator slots each).  The SHARED group 4 is
+  // computed by role 0 on even bricks and by role 1 on odd ones (the reduce pass adds the two partial sums), so both
+  // roles issue 4.5 MMAs per K step on average and the CTAs that read the same bricks stay in lockstep -- with a fixed
+  // 5 / 4 split the faster role ran ahead and the shared bricks had to be fetched from HBM again (ncu: 2.5x the operand
+  // bytes at 192x64@128^3).
+  const int ngroups = paired ? 3 : GROUPS0;
+  const int g0 = paired ? 0 : (role == 0 ? 0 : GROUPS0 - 1);
+  const int shared_slot = paired ? -1 : (role == 0 ? GROUPS0 - 1 : 0);
   if (!paired && ((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u) return;   // this role owns no needed tap group (whole CTA)
   const int tiles_d = p.tiles_d + (paired ? 1 : 0);
   const int64_t bricks = (int64_t)p.N * tiles_d * p.tiles_h * p.tiles_w;
@@ -122,6 +130,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (shared_slot >= 0) {
+    // the shared slot may not be touched by this CTA's first brick: clear it, then every MMA into it accumulates
+    if (warp >= 2) {
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(shared_slot * NCOLS);
+      for (int j = 0; j < NCOLS; j += 16) tc::tmem_st_x16_zero(taddr + (uint32_t)j);
+      tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -130,10 +149,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       for (int64_t b = b_begin; b < b_end; ++b, ++it) {
         const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
         int64_t t = b;
-        const int w0 = (int)(t % p.tiles_w) * BR_W; t /= p.tiles_w;
-        const int h0 = (int)(t % p.tiles_h) * BR_H; t /= p.tiles_h;
-        const int d0 = (int)(t % tiles_d) * p.TD - (paired ? p.TD : 0);
-        const int n = (int)(t / tiles_d);
+        // d varies fastest: consecutive bricks of a CTA share TD of the TD + 2 halo planes of S while they are still in L2
+        // (w fastest re-read them 128 bricks later, i.e. from HBM: 3.4x the operand bytes at 192x64@128^3)
+        int d0, h0, w0, n;
+        if (p.d_fastest) {
+          d0 = (int)(t % tiles_d) * p.TD - (paired ? p.TD : 0); t /= tiles_d;
+          w0 = (int)(t % p.tiles_w) * BR_W; t /= p.tiles_w;
+          h0 = (int)(t % p.tiles_h) * BR_H;
+          n = (int)(t / p.tiles_h);
+        } else {
+          w0 = (int)(t % p.tiles_w) * BR_W; t /= p.tiles_w;
+          h0 = (int)(t % p.tiles_h) * BR_H; t /= p.tiles_h;
+          d0 = (int)(t % tiles_d) * p.TD - (paired ? p.TD : 0);
+          n = (int)(t / tiles_d);
+        }
         tc::mbar_wait(&empty[st], ph ^ 1u);
         uint8_t* dst = smem + (size_t)st * stage_bytes;
         if (paired) {
@@ -177,6 +206,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         const uint64_t db0 = tc::make_smem_desc(u_addr + (uint32_t)u_bytes, (uint32_t)(2 * CS), (uint32_t)(HL_W * 2 * CS), 0,
                                                 tc::SWZ_64B);
         uint32_t acc = it != 0 ? 1u : 0u;
+        const bool shared_mine = (int)(b & 1) == role;          // which role computes the shared group for this brick
         for (int dz = 0; dz < p.TD; ++dz) {
           const uint64_t da_z = da0 + (uint64_t)((dz * 128 * 128) >> 4);
           const uint64_t db_z = db0 + (uint64_t)((dz * HL_H * HL_W * 2 * CS) >> 4);
@@ -186,8 +216,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
             const uint64_t db = db_z + (uint64_t)((hp * 2 * HL_W * 2 * CS) >> 4);
 #pragma unroll
             for (int g = 0; g < GROUPS0; ++g) {
-              if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u)))
-                tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
+              if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u))) {
+                if (g == shared_slot) {
+                  if (shared_mine) tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, 1u);
+                } else {
+                  tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
+                }
+              }
             }
             acc = 1u;
           }
@@ -244,6 +279,7 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     if (u_is_x) { cu = ci; cs = co; kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
     else { cu = co; cs = ci; }
     int role, gl, row = cu & 127;
+    bool shared = false;
     if (pair_ok && (CU - (cu >> 7) * 128) <= 64) {
       // paired-plane tile: role 0 (S window gd = 1) holds tap kd = 1 in rows 0..63 and kd = 0 in rows 64..127,
       // role 1 (gd = 2) holds kd = 2 in rows 0..63; the (kd, kh) group index inside the CTA is kh
@@ -251,9 +287,10 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
       gl = kh;
       row = (cu & 63) + (kd == 0 ? 64 : 0);
     } else {
-      const int g = kd * 3 + kh;
+      const int g = kd * 3 + kh;               // role 0: groups 0..4 in slots 0..4; role 1: groups 4..8 in slots 0..4
       role = g >= GROUPS0 ? 1 : 0;
-      gl = g - role * GROUPS0;
+      gl = g - role * (GROUPS0 - 1);
+      shared = g == GROUPS0 - 1;               // group 4: role 0 slot 4 (even bricks) + role 1 slot 0 (odd bricks)
     }
     const int tile = cu >> 7;
     const bool s1 = tile >= seg1_tile;
@@ -262,6 +299,10 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     const float* src = partial + (s1 ? seg1_offset : 0) + ((size_t)wt * 128 + row) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
     float acc = 0.f;
     for (int k = 0; k < nk; ++k) acc += src[(size_t)k * nw * 128 * PART_COLS];
+    if (shared) {                              // the other role's share: work type + 1, slot 0
+      const float* src2 = src + (size_t)128 * PART_COLS - (size_t)gl * NCOLS;
+      for (int k = 0; k < nk; ++k) acc += src2[(size_t)k * nw * 128 * PART_COLS];
+    }
     dw[i] = accumulate ? dw[i] + acc : acc;
   }
 }
@@ -336,6 +377,7 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
 
 void tc_wgrad_set_wt_fastest(int v) { g_wt_fastest = v ? 1 : 0; }
 void tc_wgrad_set_pair_planes(int v) { g_pair_planes = v ? 1 : 0; }
+void tc_wgrad_set_d_fastest(int v) { g_d_fastest = v ? 1 : 0; }
 
 bool tc_wgrad_supported(const mednet_wgrad_params* q) {
   WgPlan pl;
@@ -355,6 +397,7 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   if (enc == nullptr) return MEDNET_ENODRIVER;
   WgArgs& a = pl.a;
   a.wt_fastest = g_wt_fastest;
+  a.d_fastest = g_d_fastest;
   const void* u_ptr = pl.u_is_x ? q->b : q->a;
   const void* s_ptr = pl.u_is_x ? q->a : q->b;
   CUtensorMap map_u, map_s;
