@@ -54,3 +54,38 @@ def test_bucketed_allreduce_two_ranks(tmp_path):
     ranges = res["ranges"]
     assert ranges[0][1] == res["flat"].numel() and ranges[-1][0] == 0
     assert all(ranges[i][0] == ranges[i + 1][1] for i in range(len(ranges) - 1))   # contiguous cover, end to start
+
+
+def test_async_reported_gradients_are_counted_once():
+    """A conv weight whose gradient was enqueued on the side stream reports through the listener (`_on_async`);
+    autograd still fires its post-accumulate hook with an undefined gradient (torch >= 2.1 behaviour, measured on two
+    GPUs as every bucket being all-reduced twice).  The hook must not count it again, and must still count parameters
+    that took the synchronous path."""
+    import torch
+    from mednet_b200.parallel import BucketedAllReduce, FlatGradients
+
+    params = [torch.nn.Parameter(torch.randn(4, 3)) for _ in range(3)]
+    fg = FlatGradients(params)
+    red = BucketedAllReduce(fg.slices, fg.flat, bucket_bytes=1 << 20)
+    assert len(red.buckets) == 1 and red.buckets[0][2] == 3
+    red._on_async(params[2])             # async conv weight: listener first ...
+    red._on_hook(params[2])              # ... then autograd's hook with an undefined gradient: ignored
+    red._on_hook(params[1])
+    assert red.buckets[0][2] == 1 and red.launch_order == []
+    red._on_hook(params[0])
+    assert red.buckets[0][2] == 0 and red.launch_order == [0]
+    assert red.finish() == 1.0
+    assert red.buckets[0][2] == 3 and not red._async_reported        # re-armed
+    # the hook really fires for an undefined gradient
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            return x * 2 + 0 * w.sum()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g * 2, None
+    x = torch.ones(4, 3, requires_grad=True)
+    F.apply(x, params[0]).sum().backward()
+    assert red.buckets[0][2] == 2
+    red.remove()

@@ -57,14 +57,26 @@ class BucketedAllReduce:
             self.buckets.append([lo, hi, members, members])
         self.handles = []
         self.launch_order = []
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p, _, _ in grad_slices]
-        # conv weight gradients enqueued on the side stream (ops.wgrad_async) never pass through autograd's accumulation,
-        # so they report here; the all-reduce of a bucket is then launched BEHIND the side stream
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_hook) for p, _, _ in grad_slices]
+        # conv weight gradients enqueued on the side stream (ops.wgrad_async) bypass autograd's accumulation and report
+        # through the listener; the all-reduce of a bucket is then launched BEHIND the side stream.  autograd still calls
+        # the post-accumulate hook of such a parameter (with an undefined gradient), so the hook skips parameters that
+        # have already reported in this backward pass.
+        self._async_reported = set()
         self._ops = None
         if flat_grad.is_cuda:
             from . import ops
             self._ops = ops
-            ops.async_grad_listener = self._on_grad
+            ops.async_grad_listener = self._on_async
+
+    def _on_async(self, param):
+        self._async_reported.add(id(param))
+        self._on_grad(param)
+
+    def _on_hook(self, param):
+        if id(param) in self._async_reported:
+            return
+        self._on_grad(param)
 
     def _on_grad(self, param):
         b = self.bucket_of[id(param)]
@@ -97,6 +109,7 @@ class BucketedAllReduce:
         for h in self.handles:
             h.wait()
         self.handles.clear()
+        self._async_reported.clear()
         if self._ops is not None:
             self._ops.sync_async_wgrad()
         self.launch_order.clear()
@@ -107,7 +120,7 @@ class BucketedAllReduce:
     def remove(self):
         for h in self._hooks:
             h.remove()
-        if self._ops is not None and self._ops.async_grad_listener == self._on_grad:
+        if self._ops is not None and self._ops.async_grad_listener == self._on_async:
             self._ops.async_grad_listener = None
 
 
