@@ -37,9 +37,7 @@ def main():
             opt.zero_grad()
             DiceLoss()(net(x), y).backward()
             if reducer is not None:
-                if rank == 0:
-                    print("DEBUG overlapped", overlapped, "counters", [b[2] for b in reducer.buckets], "members",
-                          [b[3] for b in reducer.buckets], "launched", list(reducer.launch_order), flush=True)
+                assert all(b[2] == 0 for b in reducer.buckets), [b[2] for b in reducer.buckets]   # every parameter reported once
                 scale = reducer.finish()
                 assert abs(scale - 1.0 / world) < 1e-12
             else:
