@@ -3,6 +3,12 @@ midasmednet/segmentation.py:119-120, landmarks.py:176-177 -- PyTorch defaults, n
 
 All parameters are re-pointed into one contiguous buffer (and so are their gradients), so the optimiser
 step is a single kernel launch and the data-parallel all-reduce can work on bucket views of that buffer.
+
+Asynchronous weight gradients (default): the conv weights' ``.grad`` views are marked for ``ops.wgrad_async``, i.e.
+their gradients are accumulated into the flat buffer by kernels on a side stream that overlap the rest of backward.
+``step()``, ``zero_grad()`` and the data-parallel reducer join that stream themselves; code that reads ``p.grad``
+between ``backward()`` and ``step()`` (gradient clipping, logging) must call ``optimizer.sync_gradients()`` first, or
+construct the optimiser with ``async_wgrad=False``.
 """
 from __future__ import annotations
 
