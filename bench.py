@@ -372,7 +372,8 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
-        v, info = cpu_oracle_voxels_per_s(wl, steps=1, warmup=1, edge=min(wl["edge"], 64), batch=1)
+        # bounded sample of the same workload: ~10-20 s of host work (one 64^3 patch per step, 1 warm-up + 12 timed steps)
+        v, info = cpu_oracle_voxels_per_s(wl, steps=12, warmup=1, edge=min(wl["edge"], 64), batch=1)
         line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": info["sample"]}
     else:
