@@ -407,6 +407,86 @@ __global__ void __launch_bounds__(128) conv3_fewin_kernel(const T* __restrict__ 
   }
 }
 
+// Register-tiled variant of the few-input-channel stencil: one thread computes 16 output channels of FOUR consecutive
+// w-voxels, so every weight vector read from shared memory (LDS.128 = 4 output channels) feeds 16 FMAs instead of 4
+// and the six input voxels of a (kd, kh) row are loaded once.  Grid: (groups of 4 voxels per (h) row) x (n, d) x Nout/16.
+template <typename T>
+__global__ void __launch_bounds__(128) conv3_fewin4_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                           const float* __restrict__ bias, const T* __restrict__ addend,
+                                                           T* __restrict__ y, int D, int H, int W, int K, int Nout, int act,
+                                                           float act_param) {
+  constexpr int NT = 16;
+  extern __shared__ float sw[];                       // [27*K][NT] for output channels n0 .. n0+NT
+  const int n0 = blockIdx.z * NT, TK = 27 * K;
+  for (int i = threadIdx.x; i < TK * NT; i += blockDim.x) {
+    const int j = i % NT, tk = i / NT;
+    sw[i] = to_f32<T>(w[(int64_t)(n0 + j) * TK + tk]);
+  }
+  __syncthreads();
+  const int WG = (W + 3) >> 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * WG) return;
+  const int h = q / WG, w0 = (q - h * WG) * 4;
+  const int n = blockIdx.y / D, d = blockIdx.y - n * D;
+  float acc[4][NT];
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[v][j] = bias != nullptr ? bias[n0 + j] : 0.f;
+  for (int kd = 0; kd < 3; ++kd) {
+    const int id = d + kd - 1;
+    if (id < 0 || id >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = h + kh - 1;
+      if (ih < 0 || ih >= H) continue;
+      const T* xrow = x + (((int64_t)n * D + id) * H + ih) * (int64_t)W * K;
+      for (int k = 0; k < K; ++k) {
+        float xv[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int iw = w0 - 1 + i;
+          xv[i] = (iw >= 0 && iw < W) ? to_f32<T>(xrow[(int64_t)iw * K + k]) : 0.f;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wr = sw + (size_t)(((kd * 3 + kh) * 3 + kw) * K + k) * NT;
+#pragma unroll
+          for (int j = 0; j < NT; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc[v][j] = fmaf(xv[v + kw], wv.x, acc[v][j]);
+              acc[v][j + 1] = fmaf(xv[v + kw], wv.y, acc[v][j + 1]);
+              acc[v][j + 2] = fmaf(xv[v + kw], wv.z, acc[v][j + 2]);
+              acc[v][j + 3] = fmaf(xv[v + kw], wv.w, acc[v][j + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int64_t vox0 = (((int64_t)n * D + d) * H + h) * W + w0;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    if (w0 + v >= W) break;
+#pragma unroll
+    for (int j = 0; j < NT; j += 8) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = acc[v][j + i];
+      if (addend != nullptr) {
+        float a8[8];
+        load_vec<T, 8>(addend + (vox0 + v) * Nout + n0 + j, a8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += a8[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = act_apply(o[i], act, act_param);
+      store_vec<T, 8>(y + (vox0 + v) * Nout + n0 + j, o);
+    }
+  }
+}
+
 // few OUTPUT channels (Nout <= 4, K = 8 * TPV): TPV threads per voxel, each owns 8 input channels (one 16-byte
 // load per tap: a warp reads whole cache lines), partial dot products combined with warp shuffles
 template <typename T, int TPV>
@@ -834,7 +914,12 @@ int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int ac
 template <typename T>
 static int small_fprop_t(const mednet_conv3d_params* p, cudaStream_t st) {
   const int HW = p->Ho * p->Wo;
-  if (fewin_fprop_ok(p)) {
+  if (fewin_fprop_ok(p) && p->Nout % 16 == 0 && p->Wo >= 4) {
+    dim3 grid(ceil_div(p->Ho * ceil_div(p->Wo, 4), 128), (unsigned)(p->N * p->Do), p->Nout / 16);
+    const size_t smem = (size_t)27 * p->K * 16 * sizeof(float);
+    conv3_fewin4_kernel<T><<<grid, 128, smem, st>>>((const T*)p->x, (const T*)p->w, p->bias, (const T*)p->addend, (T*)p->y,
+                                                    p->Do, p->Ho, p->Wo, p->K, p->Nout, p->act, p->act_param);
+  } else if (fewin_fprop_ok(p)) {
     const int NT = p->Nout % 32 == 0 ? 32 : (p->Nout % 16 == 0 ? 16 : 8);
     dim3 grid(ceil_div(HW, 128), (unsigned)(p->N * p->Do), p->Nout / NT);
     const size_t smem = (size_t)27 * p->K * NT * sizeof(float);

@@ -90,51 +90,52 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
   }
 }
 
-// One thread per POOLED voxel x channel vector: reads dy / argmax code (/ y) once and writes the 8 children (the
-// gradient at the argmax, zero elsewhere).  Odd trailing planes/rows/columns of the input (floor mode) get zeros from
-// the threads of the last pooled plane/row/column.
+// One block per input LINE (n, d, h): thread (tx, ty) owns channel vector tx and walks w = ty, ty + R, ...  Reads of the
+// skip-path gradient (addend) and writes of dx are fully coalesced rows; the pooled gradient / argmax code / pooled value
+// of the parent voxel are read 8 times (by its 8 children) out of L1/L2.  No per-element index division.
 template <typename T, int V>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dx,
                                    int N, int D, int H, int W, int C, const T* __restrict__ y, int in_act,
                                    float in_act_param, const T* __restrict__ addend) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2, ncol = C / V;
-  const int64_t total = (int64_t)N * Do * Ho * Wo * ncol;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % ncol);
-    int64_t t = i / ncol;
-    const int ow = (int)(t % Wo); t /= Wo;
-    const int oh = (int)(t % Ho); t /= Ho;
-    const int od = (int)(t % Do);
-    const int n = (int)(t / Do);
-    float gy[V];
-    load_vec<T, V>(dy + i * V, gy);
-    if (in_act != MEDNET_ACT_NONE) {     // deferred derivative of the producer's activation: x[argmax] == y
-      float yv[V];
-      load_vec<T, V>(y + i * V, yv);
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv >= ncol) return;
+  const int line = blockIdx.x;                       // (n * D + d) * H + h
+  const int h = line % H, nd = line / H, d = nd % D, n = nd / D;
+  const int od = d >> 1, oh = h >> 1;
+  const bool line_in = od < Do && oh < Ho;
+  const int dh_code = ((d & 1) << 2) | ((h & 1) << 1);
+  const int64_t lbase = (int64_t)line * W * C + cv * V;
+  const int64_t pbase = (((int64_t)n * Do + od) * Ho + oh) * (int64_t)Wo * C + cv * V;
+  for (int w = threadIdx.y; w < W; w += blockDim.y) {
+    float g[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) gy[j] *= act_grad_from_out(yv[j], in_act, in_act_param);
+    for (int j = 0; j < V; ++j) g[j] = 0.f;
+    const int ow = w >> 1;
+    if (line_in && ow < Wo) {
+      const int64_t o = pbase + (int64_t)ow * C;
+      const int mine = dh_code | (w & 1);
+      float gy[V];
+      load_vec<T, V>(dy + o, gy);
+      union { typename RawVec<V>::type r; uint8_t b[V]; } u;
+      u.r = *reinterpret_cast<const typename RawVec<V>::type*>(idx + o);
+      if (in_act != MEDNET_ACT_NONE) {     // deferred derivative of the producer's activation: x[argmax] == y
+        float yv[V];
+        load_vec<T, V>(y + o, yv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) gy[j] *= act_grad_from_out(yv[j], in_act, in_act_param);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = (u.b[j] == mine) ? gy[j] : 0.f;
     }
-    union { typename RawVec<V>::type r; uint8_t b[V]; } u;
-    u.r = *reinterpret_cast<const typename RawVec<V>::type*>(idx + i * V);
-    // children; the last pooled index along an odd axis also clears the unpooled remainder
-    const int dz1 = (od == Do - 1) ? D - 2 * od : 2, dy1 = (oh == Ho - 1) ? H - 2 * oh : 2, dx1 = (ow == Wo - 1) ? W - 2 * ow : 2;
-    for (int dz = 0; dz < dz1; ++dz)
-      for (int dyy = 0; dyy < dy1; ++dyy)
-        for (int dxx = 0; dxx < dx1; ++dxx) {
-          const int code = (dz << 2) | (dyy << 1) | dxx;
-          const bool inside = dz < 2 && dyy < 2 && dxx < 2;
-          float g[V];
+    const int64_t off = lbase + (int64_t)w * C;
+    if (addend != nullptr) {
+      float a[V];
+      load_vec<T, V>(addend + off, a);
 #pragma unroll
-          for (int j = 0; j < V; ++j) g[j] = (inside && u.b[j] == code) ? gy[j] : 0.f;
-          const int64_t off = ((((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dyy)) * W + (2 * ow + dxx)) * C + cv * V;
-          if (addend != nullptr) {
-            float a[V];
-            load_vec<T, V>(addend + off, a);
-#pragma unroll
-            for (int j = 0; j < V; ++j) g[j] += a[j];
-          }
-          store_vec<T, V>(dx + off, g);
-        }
+      for (int j = 0; j < V; ++j) g[j] += a[j];
+    }
+    store_vec<T, V>(dx + off, g);
   }
 }
 
@@ -319,11 +320,17 @@ extern "C" int mednet_maxpool3d_bwd(const mednet_pool_bwd_params* p, mednet_stre
   MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
   MEDNET_REQUIRE(p->N > 0 && p->C > 0 && p->D >= 2 && p->H >= 2 && p->W >= 2, MEDNET_EINVAL);
   const int V = pick_vec(p->C, dtype_bytes(p->dtype));
-  const int64_t total = (int64_t)p->N * (p->D / 2) * (p->H / 2) * (p->W / 2) * (p->C / V);
+  const int ncol = p->C / V;
+  const int ncol_t = ncol < 256 ? ncol : 256;
+  int R = 256 / ncol_t;
+  if (R > p->W) R = p->W;
+  if (R < 1) R = 1;
+  const int64_t lines = (int64_t)p->N * p->D * p->H;
+  MEDNET_REQUIRE(lines < ((int64_t)1 << 31) && ceil_div(ncol, ncol_t) <= 65535, MEDNET_EUNSUPPORTED);
+  dim3 grid((unsigned)lines, (unsigned)ceil_div(ncol, ncol_t)), block(ncol_t, R);
   MEDNET_DISPATCH_TV(p->dtype, V, {
-    maxpool_bwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->dy, p->idx, (T*)p->dx, p->N, p->D,
-                                                                       p->H, p->W, p->C, (const T*)p->y, p->in_act,
-                                                                       p->in_act_param, (const T*)p->addend);
+    maxpool_bwd_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->dy, p->idx, (T*)p->dx, p->N, p->D, p->H, p->W, p->C,
+                                                          (const T*)p->y, p->in_act, p->in_act_param, (const T*)p->addend);
   });
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
