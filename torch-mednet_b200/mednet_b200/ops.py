@@ -638,6 +638,7 @@ class Conv3x3Fn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[1]
         sp = tuple(x.shape[1:4])
         ctx.cin_real = cin
+        weight_eff = weight
         if FIRST_LAYER_PAD and cin < FIRST_LAYER_PAD and x.dtype == torch.bfloat16 and impl != "simt" and cout % 16 == 0:
             padded_shape = tuple(x.shape[:-1]) + (FIRST_LAYER_PAD,)
             if conv_select_impl(padded_shape, sp, FIRST_LAYER_PAD, cout, x.dtype, 0, impl) == 2:
@@ -647,8 +648,6 @@ class Conv3x3Fn(torch.autograd.Function):
                 w16 = weight.new_zeros((cout, FIRST_LAYER_PAD, 3, 3, 3))
                 w16[:, :cin] = weight.detach()
                 weight_eff, cin = w16, FIRST_LAYER_PAD
-        if cin == ctx.cin_real:
-            weight_eff = weight
         impl_id = conv_select_impl(x.shape, sp, cin, cout, x.dtype, 0, impl, x.data_ptr(), 0, 0)
         wp = k_pack_weights(weight_eff, cin, cout, x.dtype, 2 if impl_id == 2 else 0)
         add = _c(addend) if addend is not None else None
@@ -656,7 +655,7 @@ class Conv3x3Fn(torch.autograd.Function):
                     addend=add, act=act)
         bwd_act = 0 if defer_act else act
         ctx.weight_ref = weight                      # the Parameter itself (its .grad buffer may be written asynchronously)
-        ctx.save_for_backward(x, weight_eff.detach() if cin != ctx.cin_real else weight, y if bwd_act else None)
+        ctx.save_for_backward(x, weight_eff, y if bwd_act else None)
         ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = bwd_act, impl, bias is not None, addend is not None
         return y
 
