@@ -412,6 +412,9 @@ typedef struct {
   void*       tiles;      /* [B, P0,P1,P2, C] NDHWC tiles, dtype dst_dtype                  */
   const int32_t* origins; /* [B, 3] device array of tile origins in PADDED coordinates      */
   int32_t B, C, X, Y, Z, P0, P1, P2, O0, O1, O2, src_dtype, dst_dtype;
+  int32_t ncdhw_out;      /* 0: tiles [B, P0,P1,P2, C] (NDHWC, network input); 1: tiles [B, C, P0,P1,P2] (label / heatmap
+                             crops of the GPU-resident patch sampler, ref mm/dataset.py:315-336).  MEDNET_U8 -> MEDNET_U8 is
+                             supported in addition to the float dtypes. */
 } mednet_tile_gather_params;
 int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_stream_t stream);
 typedef struct {

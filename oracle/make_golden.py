@@ -134,6 +134,36 @@ def golden_tiling():
     np.savez_compressed(os.path.join(OUT, "tiling.npz"), **out)
 
 
+def golden_sampling():
+    """Patch positions from the reference's own get_labeled_position / get_random_patch_indices (dataset.py:18-88),
+    function bodies extracted with ast; ``np.int`` (removed from NumPy) is mapped to ``int``."""
+    src = open(os.path.join(REF, "midasmednet", "dataset.py")).read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and
+           n.name in ("get_labeled_position", "get_random_patch_indices")]
+    np_shim = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    np_shim.int = int
+    ns = {"np": np_shim}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "dataset.py", "exec"), ns)
+    rng = np.random.default_rng(5)
+    label = np.zeros((40, 37, 29), dtype=np.uint8)
+    label[5:12, 20:30, 3:9] = 1
+    label[30:38, 2:9, 15:27] = 2
+    label[(rng.random(label.shape) < 0.002)] = 1
+    patch = np.array([16, 12, 10])
+    probs = np.array([0.2, 0.5, 0.3])
+    np.random.seed(77)
+    ini, cls = [], []
+    for _ in range(64):
+        c = np.random.choice(range(len(probs)), p=probs / probs.sum())           # dataset.py:301-302
+        pos = ns["get_labeled_position"](label, c, label_any=np.any(label == c, axis=2)) if c > 0 else None
+        a, b = ns["get_random_patch_indices"](patch, np.array(label.shape), pos=pos)
+        assert np.array_equal(b - a, patch)
+        ini.append(a)
+        cls.append(c)
+    np.savez_compressed(os.path.join(OUT, "sampling.npz"), label=label, patch=patch, probs=probs, seed=77,
+                        index_ini=np.array(ini), selected_class=np.array(cls))
+
+
 def golden_semantics():
     """KATs probed by the survey (last row), recorded from live torch."""
     import torch.nn.functional as F
@@ -163,6 +193,7 @@ def main():
     golden_residual(rmodel, rloss)
     golden_tiling()
     golden_semantics()
+    golden_sampling()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/make_golden.py from {REF} with torch {torch.__version__}, numpy {np.__version__}\n")
     print("golden vectors written to", os.path.abspath(OUT))

@@ -1,0 +1,93 @@
+"""GPU-resident patch sampler: device crops bit-exact against the oracle's NumPy crop (midasmednet/dataset.py:315-336)
+at the positions the host sampler drew, and the batch feeds the training step unchanged."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampling as osamp
+
+pytestmark = pytest.mark.gpu
+
+
+def _cohort(seed=0, heatmaps=True):
+    rs = np.random.RandomState(seed)
+    shapes = [(40, 37, 29), (33, 48, 36), (64, 32, 40)]
+    images = [rs.randn(2, *s).astype(np.float32) for s in shapes]
+    labels = [(rs.rand(1, *s) > 0.8).astype(np.uint8) * rs.randint(1, 3, size=(1,) + s).astype(np.uint8) for s in shapes]
+    hms = [rs.randint(0, 256, size=(3,) + s).astype(np.uint8) for s in shapes] if heatmaps else None
+    return images, labels, hms
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("heatmaps", [False, True])
+def test_batch_matches_oracle_crops(dtype, heatmaps):
+    from mednet_b200.sampler import GpuMedDataset
+    images, labels, hms = _cohort(1, heatmaps)
+    P = [16, 24, 8]
+    ds = GpuMedDataset(images, labels, samples_per_subject=4, patch_size=P, heatmaps=hms,
+                       class_probabilities=[0.2, 0.5, 0.3], data_dtype=dtype, rng=np.random.RandomState(11))
+    assert len(ds) == 12
+    batch = ds.batch(range(7))
+    data, label = batch["data"], batch["label"]
+    assert data.shape == (7, 2, *P) and data.dtype == dtype and data.permute(0, 2, 3, 4, 1).is_contiguous()
+    assert label.shape == (7, (3 if heatmaps else 0) + 1, *P) and label.dtype == torch.uint8
+    for b in range(7):
+        s = b % 3
+        assert batch["subject_key"][b] == str(s)
+        full = np.concatenate([hms[s], labels[s]], axis=0) if heatmaps else labels[s]
+        want_d, want_l = osamp.crop_patch(images[s], full, batch["patch_position"][b], P)
+        want_d = torch.from_numpy(want_d).to(dtype)                      # bf16: one round-to-nearest-even, as the kernel
+        assert torch.equal(data[b].cpu(), want_d)
+        assert np.array_equal(label[b].cpu().numpy(), want_l)
+        cls = batch["selected_class"][b]
+        if cls > 0:
+            assert (want_l[-1] == cls).any()
+
+
+def test_positions_equal_the_host_oracle_sequence():
+    """The product draws from np.random in the reference's order: replaying the oracle with the same seed gives the
+    same positions, for several subjects of different shape."""
+    from mednet_b200.sampler import GpuMedDataset
+    images, labels, _ = _cohort(2, False)
+    P, probs = [12, 12, 12], [0.3, 0.3, 0.4]
+    ds = GpuMedDataset(images, labels, 5, P, class_probabilities=probs, rng=np.random.RandomState(99))
+    got = [ds.sample_position(i) for i in range(15)]
+    np.random.seed(99)
+    for i, (subject, ini, cls) in enumerate(got):
+        lab = labels[i % 3][0]
+        o_ini, o_cls = osamp.sample_patch_position(lab, P, probs, osamp.label_any_maps(lab, 3))
+        assert subject == i % 3 and cls == o_cls and np.array_equal(ini, o_ini)
+
+
+def test_getitem_contract_and_loader_epoch():
+    from mednet_b200.sampler import GpuMedDataset
+    images, labels, hms = _cohort(3, True)
+    ds = GpuMedDataset(images, labels, 2, [8, 8, 8], heatmaps=hms, rng=np.random.RandomState(0))
+    item = ds[4]
+    assert item["data"].shape == (2, 8, 8, 8) and item["label"].shape == (4, 8, 8, 8)
+    assert item["subject_key"] == "1" and item["selected_class"] == 0 and item["patch_position"].shape == (3,)
+    sizes = [b["data"].shape[0] for b in ds.loader(4, shuffle=True)]
+    assert sizes == [4, 2]
+    assert [b["data"].shape[0] for b in ds.loader(4, shuffle=False, drop_last=True)] == [4]
+
+
+def test_sampler_feeds_training_step():
+    from mednet_b200.sampler import GpuMedDataset
+    rs = np.random.RandomState(0)
+    images = [rs.randn(1, 48, 40, 36).astype(np.float32) for _ in range(2)]
+    labels = [(rs.rand(1, 48, 40, 36) > 0.7).astype(np.uint8) for _ in range(2)]
+    ds = GpuMedDataset(images, labels, 4, [32, 32, 32], class_probabilities=[0.5, 0.5], rng=np.random.RandomState(1))
+    import argparse
+    from mednet_b200.segmentation import SegmentationUNet3D
+    hp = argparse.Namespace(in_channels=1, out_channels=2, fmaps=[16, 32], learning_rate=1e-3, num_workers=0,
+                            batch_size=2, loss="DICE", loss_weight=[0.5, 0.5])
+    net = SegmentationUNet3D(hp).cuda()
+    opt = net.configure_optimizers()
+    losses = []
+    for batch in ds.loader(2, shuffle=True):
+        opt.zero_grad()
+        out = net.training_step(batch, 0)
+        out["loss"].backward()
+        opt.step()
+        losses.append(float(out["loss"].detach()))
+    assert len(losses) == 4 and all(np.isfinite(losses))

@@ -37,6 +37,7 @@ template <> __device__ __forceinline__ float to_f32<uint8_t>(uint8_t v) { return
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ uint8_t from_f32<uint8_t>(float v) { return (uint8_t)v; }
 
 // ------------------------------------------------------------------------------------------------
 // V-wide vector load/store (V * sizeof(T) in {2,4,8,16} bytes, naturally aligned)

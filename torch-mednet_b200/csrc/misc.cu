@@ -170,10 +170,18 @@ __global__ void tile_gather_kernel(const TS* __restrict__ vol, TD* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / per_tile);
     int64_t t = i - (int64_t)b * per_tile;
-    const int c = (int)(t % p.C); t /= p.C;
-    const int z = (int)(t % p.P2); t /= p.P2;
-    const int y = (int)(t % p.P1);
-    const int x = (int)(t / p.P1);
+    int c, x, y, z;
+    if (p.ncdhw_out) {                         // [B, C, P0, P1, P2]
+      z = (int)(t % p.P2); t /= p.P2;
+      y = (int)(t % p.P1); t /= p.P1;
+      x = (int)(t % p.P0);
+      c = (int)(t / p.P0);
+    } else {                                   // [B, P0, P1, P2, C]
+      c = (int)(t % p.C); t /= p.C;
+      z = (int)(t % p.P2); t /= p.P2;
+      y = (int)(t % p.P1);
+      x = (int)(t / p.P1);
+    }
     // padded coordinate -> original coordinate (low pad = overlap); outside -> constant 0 (predict.py:68)
     const int gx = org[b * 3 + 0] + x - p.O0, gy = org[b * 3 + 1] + y - p.O1, gz = org[b * 3 + 2] + z - p.O2;
     float v = 0.f;
@@ -295,9 +303,14 @@ extern "C" int mednet_landmark_extract(const mednet_landmark_params* p, void* wo
 
 extern "C" int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->volume && p->tiles && p->origins && p->B > 0 && p->C > 0, MEDNET_EINVAL);
-  MEDNET_REQUIRE(dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype), MEDNET_EUNSUPPORTED);
   const int64_t total = (int64_t)p->B * p->C * p->P0 * p->P1 * p->P2;
   const int nb = grid_for(total, 256);
+  if (p->src_dtype == MEDNET_U8 && p->dst_dtype == MEDNET_U8) {
+    tile_gather_kernel<uint8_t, uint8_t><<<nb, 256, 0, stream>>>((const uint8_t*)p->volume, (uint8_t*)p->tiles, p->origins, *p);
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  }
+  MEDNET_REQUIRE(dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype), MEDNET_EUNSUPPORTED);
   if (p->src_dtype == MEDNET_F32 && p->dst_dtype == MEDNET_F32)
     tile_gather_kernel<float, float><<<nb, 256, 0, stream>>>((const float*)p->volume, (float*)p->tiles, p->origins, *p);
   else if (p->src_dtype == MEDNET_F32)

@@ -7,6 +7,7 @@ Drop-in surface (same names as the reference package ``midasmednet``):
     from mednet_b200.segmentation import SegmentationNet
     from mednet_b200.landmarks import LandmarkNet
     from mednet_b200.dataset import grid_patch_generator
+    from mednet_b200.sampler import GpuMedDataset          # MedDataset's random patches from HBM-resident volumes
 
 ``install_as_midasmednet()`` registers these modules under the reference's import paths so that unmodified
 caller code (``from midasmednet.unet.model import UNet3D``) picks up the CUDA implementation.

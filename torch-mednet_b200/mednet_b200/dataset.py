@@ -1,7 +1,7 @@
 """Sliding-window tiling geometry of the reference (midasmednet/dataset.py:349-389, :444-474) and the
-synthetic datasets used for measurement.  The HDF5/zarr readers and the random-patch MedDataset
-(dataset.py:109-346) are host-side I/O and out of scope; the synthetic
-datasets emit batches with exactly MedDataset's dict contract (dataset.py:332-346).
+synthetic datasets used for measurement.  The HDF5/zarr readers (dataset.py:109-260) are host-side I/O and out of
+scope; MedDataset's random patch sampling lives in ``sampler.py`` (device-resident);
+the synthetic datasets emit batches with exactly MedDataset's dict contract (dataset.py:332-346).
 """
 from __future__ import annotations
 
