@@ -12,7 +12,7 @@ import logging
 import numpy as np
 import torch
 
-from _common import experiment_parser, parse_with_config, require_dataset
+from _common import experiment_parser, parse_with_config, require_dataset, seed_everything, synthetic_cohort
 
 
 def main(argv=None):
@@ -23,15 +23,24 @@ def main(argv=None):
     parser = LandmarkNet.add_model_specific_args(experiment_parser("aorth_ldmks", heatmaps=True))
     parser = __import__("argparse").ArgumentParser(parents=[parser], description=__doc__)
     hparams = parse_with_config(parser, argv)
-    torch.manual_seed(hparams.seed)
-    np.random.seed(hparams.seed)
+    seed_everything(hparams.seed)
     logging.getLogger().setLevel("INFO")                 # train_ldmks.py:70
     require_dataset(hparams, "train_ldmks")
     L = len(hparams.loss_regression_weight)
     K = hparams.out_channels - L
     if K < 2:
         raise SystemExit(f"out_channels ({hparams.out_channels}) must be >= len(loss_regression_weight) ({L}) + 2 classes")
-    mk = lambda n, seed: SyntheticSegmentationDataset(n, hparams.patch_size, hparams.in_channels, K, num_heatmaps=L, seed=seed)
+    if hparams.gpu_sampler:                              # MedDataset(..., heatmap_group) of train_ldmks.py, volumes in HBM
+        from mednet_b200.sampler import GpuMedDataset
+        dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
+
+        def mk(n, seed):
+            images, labels, hms = synthetic_cohort(n, hparams.gpu_sampler, hparams.in_channels, K, L, seed=seed)
+            return GpuMedDataset(images, labels, hparams.patches_per_subject, hparams.patch_size, heatmaps=hms,
+                                 class_probabilities=hparams.class_probabilities, device=dev)
+    else:
+        def mk(n, seed):
+            return SyntheticSegmentationDataset(n, hparams.patch_size, hparams.in_channels, K, num_heatmaps=L, seed=seed)
     cls = LandmarkUNet3D if hparams.arch == "unet3d" else LandmarkNet
     model = cls(hparams, training_dataset=mk(hparams.synthetic, hparams.seed),
                 validation_dataset=mk(max(1, hparams.synthetic // 4), hparams.seed + 1))

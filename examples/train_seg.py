@@ -3,6 +3,8 @@
 seeds :61-65, datasets :98-118, module :120-122, Trainer(gpus, max_epochs, default_root_dir, resume) :123-133).
 
     python examples/train_seg.py --synthetic 16 --patch_size 64 64 64 --batch_size 2 --max_epochs 1 --model_dir /tmp/m
+    python examples/train_seg.py --synthetic 4 --gpu_sampler 160 160 128 --class_probabilities 0.3 0.7 \
+           --patches_per_subject 8 --patch_size 64 64 64 --batch_size 2 --max_epochs 1   # patches drawn from HBM-resident volumes
     torchrun --nproc-per-node 8 examples/train_seg.py --gpus 8 --synthetic 64 ...       # data parallel
 """
 import logging
@@ -10,7 +12,7 @@ import logging
 import numpy as np
 import torch
 
-from _common import experiment_parser, parse_with_config, require_dataset
+from _common import experiment_parser, parse_with_config, require_dataset, seed_everything, synthetic_cohort
 
 
 def main(argv=None):
@@ -21,14 +23,23 @@ def main(argv=None):
     parser = SegmentationNet.add_model_specific_args(experiment_parser("aorth"))
     parser = __import__("argparse").ArgumentParser(parents=[parser], description=__doc__)
     hparams = parse_with_config(parser, argv)
-    torch.manual_seed(hparams.seed)                      # train_seg.py:61-65 (the kernels are deterministic by construction)
-    np.random.seed(hparams.seed)
+    seed_everything(hparams.seed)                        # train_seg.py:61-65 (the kernels are deterministic by construction)
     logging.getLogger().setLevel(hparams.log_level)
     require_dataset(hparams, "train_seg")
-    train_ds = SyntheticSegmentationDataset(hparams.synthetic, hparams.patch_size, hparams.in_channels,
-                                            hparams.out_channels, seed=hparams.seed)
-    val_ds = SyntheticSegmentationDataset(max(1, hparams.synthetic // 4), hparams.patch_size, hparams.in_channels,
-                                          hparams.out_channels, seed=hparams.seed + 1)
+    if hparams.gpu_sampler:                              # MedDataset(...) of train_seg.py:98-118, volumes in HBM
+        from mednet_b200.sampler import GpuMedDataset
+        dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
+
+        def cohort(n, seed):
+            images, labels, _ = synthetic_cohort(n, hparams.gpu_sampler, hparams.in_channels, hparams.out_channels, seed=seed)
+            return GpuMedDataset(images, labels, hparams.patches_per_subject, hparams.patch_size,
+                                 class_probabilities=hparams.class_probabilities, device=dev)
+        train_ds, val_ds = cohort(hparams.synthetic, hparams.seed), cohort(max(1, hparams.synthetic // 4), hparams.seed + 1)
+    else:
+        train_ds = SyntheticSegmentationDataset(hparams.synthetic, hparams.patch_size, hparams.in_channels,
+                                                hparams.out_channels, seed=hparams.seed)
+        val_ds = SyntheticSegmentationDataset(max(1, hparams.synthetic // 4), hparams.patch_size, hparams.in_channels,
+                                              hparams.out_channels, seed=hparams.seed + 1)
     cls = SegmentationUNet3D if hparams.arch == "unet3d" else SegmentationNet
     model = cls(hparams, training_dataset=train_ds, validation_dataset=val_ds)
     trainer = Trainer(gpus=hparams.gpus, max_epochs=hparams.max_epochs, default_root_dir=hparams.model_dir,

@@ -70,3 +70,18 @@ def test_train_then_predict_entry_points(tmp_path):
                         "32", "32", "32", "--patch_size", "32", "32", "32", "--patch_overlap", "4", "4", "4", "--sigma",
                         "3", "3", "3"])
     assert tuple(out.shape) == (4, 32, 32, 32)
+
+
+@pytest.mark.gpu
+def test_training_entry_points_with_the_gpu_resident_sampler(tmp_path):
+    """--gpu_sampler: patches drawn by the device-resident MedDataset (class-balanced positions, heatmaps + class map)."""
+    import train_ldmks
+    import train_seg
+    tr = train_seg.main(["--synthetic", "3", "--gpu_sampler", "48", "40", "36", "--class_probabilities", "0.3", "0.7",
+                         "--patches_per_subject", "2", "--patch_size", "32", "32", "32", "--batch_size", "2",
+                         "--fmaps", "8", "--out_channels", "2", "--max_epochs", "1", "--model_dir", str(tmp_path / "s")])
+    assert tr.history and all(np.isfinite(list(h.values())).all() for h in tr.history)
+    tr = train_ldmks.main(["--synthetic", "2", "--gpu_sampler", "40", "40", "40", "--patches_per_subject", "2",
+                           "--patch_size", "32", "32", "32", "--batch_size", "2", "--fmaps", "8", "--out_channels", "4",
+                           "--loss_regression_weight", "0.01", "0.01", "--max_epochs", "1", "--arch", "unet3d"])
+    assert tr.history

@@ -89,3 +89,40 @@ def test_async_reported_gradients_are_counted_once():
     F.apply(x, params[0]).sum().backward()
     assert red.buckets[0][2] == 2
     red.remove()
+
+
+def _loader_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "torch-mednet_b200"))
+    from mednet_b200.dataset import SyntheticSegmentationDataset
+    from mednet_b200.parallel import sharded_loader
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ds = SyntheticSegmentationDataset(11, (4, 4, 4))
+    seen = []
+    for epoch in range(2):
+        batches = [b["data"] for b in sharded_loader(ds, 2, shuffle=True, epoch=epoch)]      # rank/world from the group
+        seen.append(torch.cat(batches))
+    torch.save(seen, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_each_rank_gets_its_own_share_of_an_epoch(tmp_path):
+    """Patch batches are the unit of data parallelism: with the same seed on every rank the hooks must still hand
+    different samples to different ranks, the same number of them, and reshuffle per epoch."""
+    from mednet_b200.dataset import SyntheticSegmentationDataset
+    from mednet_b200.parallel import epoch_order
+    out = str(tmp_path / "seen")
+    mp.spawn(_loader_worker, args=(2, 29500 + (os.getpid() % 2000) + 1, out), nprocs=2, join=True)
+    a, b = torch.load(out + ".0"), torch.load(out + ".1")
+    ds = SyntheticSegmentationDataset(11, (4, 4, 4))
+    every = torch.stack([ds[i]["data"] for i in range(11)])
+
+    def ids(t):
+        return [int((every == p).flatten(1).all(1).nonzero()) for p in t]
+    for epoch in range(2):
+        ia, ib = ids(a[epoch]), ids(b[epoch])
+        assert len(ia) == len(ib) == 5 and not set(ia) & set(ib)              # 11 -> 10 samples, 5 each, disjoint
+        assert ia == epoch_order(11, True, epoch, 0, 0, 2).tolist()
+    assert ids(a[0]) != ids(a[1])
+    assert epoch_order(7, False, 0).tolist() == list(range(7))
+    assert sorted(epoch_order(9, True, 3, rank=0, world=1).tolist()) == list(range(9))

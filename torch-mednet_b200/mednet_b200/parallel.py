@@ -141,3 +141,38 @@ def init_distributed(backend=None):
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, local, world
+
+
+def rank_and_world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def epoch_order(n, shuffle, epoch, seed=0, rank=0, world=1):
+    """Sample order of one epoch for one rank: a permutation every rank derives identically (torch generator seeded
+    with seed + epoch, the rule of torch's DistributedSampler), truncated to a multiple of ``world`` so that all ranks
+    run the same number of steps (their collectives pair up), then taken with stride ``world``."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(int(seed) + int(epoch))
+        order = torch.randperm(n, generator=g).numpy()
+    else:
+        import numpy as np
+        order = np.arange(n)
+    if world > 1:
+        order = order[:n - n % world][rank::world]
+    return order
+
+
+def sharded_loader(dataset, batch_size, num_workers=0, shuffle=True, epoch=0, seed=0, rank=None, world=None):
+    """The loader a task module's train/val_dataloader hook returns (segmentation.py:122-132): patch batches are the
+    unit of data parallelism, so each rank must see its own share of an epoch.  A device-resident dataset
+    (``sampler.GpuMedDataset``) iterates itself; anything else goes through a DataLoader over this rank's indices."""
+    from torch.utils.data import DataLoader, Subset
+    if rank is None or world is None:
+        rank, world = rank_and_world()
+    if hasattr(dataset, "loader"):
+        return dataset.loader(batch_size, shuffle=shuffle, epoch=epoch, seed=seed, rank=rank, world=world)
+    if world == 1:
+        return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, shuffle=shuffle)
+    order = epoch_order(len(dataset), shuffle, epoch, seed, rank, world)
+    return DataLoader(Subset(dataset, order.tolist()), batch_size=batch_size, num_workers=num_workers, shuffle=False)

@@ -182,10 +182,13 @@ class GpuMedDataset:
         patch = self.batch([idx])
         return {k: (v[0] if k != "label" and k != "data" else v.squeeze(0)) for k, v in patch.items()}
 
-    def loader(self, batch_size, shuffle=True, drop_last=False):
-        """Iterates one epoch like ``DataLoader(dataset, batch_size, shuffle)`` (segmentation.py:129-134), without
-        worker processes: sampling is a few host draws plus asynchronous launches."""
-        order = self.rng.permutation(len(self)) if shuffle else np.arange(len(self))
+    def loader(self, batch_size, shuffle=True, drop_last=False, epoch=0, seed=0, rank=0, world=1):
+        """One epoch like ``DataLoader(dataset, batch_size, shuffle)`` (segmentation.py:122-127) without worker
+        processes: a few host draws and asynchronous launches per batch.  As with the DataLoader, the visiting ORDER
+        comes from a torch generator and the patch positions from NumPy's; ``rank``/``world`` give each data-parallel
+        rank its share (seed NumPy differently per rank, or the ranks draw the same relative positions)."""
+        from .parallel import epoch_order
+        order = epoch_order(len(self), shuffle, epoch, seed, rank, world)
         for b0 in range(0, len(order), batch_size):
             chunk = order[b0:b0 + batch_size]
             if drop_last and len(chunk) < batch_size:

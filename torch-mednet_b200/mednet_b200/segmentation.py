@@ -11,9 +11,9 @@ import argparse
 import logging
 
 import torch
-from torch.utils.data import DataLoader
 
 from .optim import FusedAdam
+from .parallel import sharded_loader
 from .unet.loss import CrossEntropyLoss, DiceLoss, dice_metric
 from .unet.model import ResidualUNet3D, UNet3D
 
@@ -27,11 +27,12 @@ class _TaskMixin:
         return FusedAdam(self.parameters(), lr=self.learning_rate)
 
     def train_dataloader(self):
-        return DataLoader(self.training_dataset, batch_size=self.batch_size, num_workers=self.num_workers, shuffle=True)
+        """segmentation.py:122-127; under torch.distributed every rank gets its own share of the epoch."""
+        return sharded_loader(self.training_dataset, self.batch_size, self.num_workers, shuffle=True,
+                              epoch=getattr(self, "current_epoch", 0))
 
     def val_dataloader(self):
-        return DataLoader(self.validation_dataset, batch_size=self.batch_size, num_workers=self.num_workers,
-                          shuffle=False)
+        return sharded_loader(self.validation_dataset, self.batch_size, self.num_workers, shuffle=False)
 
 
 def _segmentation_class(base):

@@ -60,7 +60,13 @@ class Trainer:
                     for i, batch in enumerate(model.val_dataloader()):
                         outs.append(model.validation_step(_to_device(batch, dev), i))
                 if outs:
-                    self.history.append({k: float(v) for k, v in model.validation_epoch_end(outs)["log"].items()})
+                    logs = model.validation_epoch_end(outs)["log"]
+                    if world > 1:                              # every rank validated its own share: average them
+                        import torch.distributed as dist
+                        vals = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=dev) for v in logs.values()])
+                        dist.all_reduce(vals)
+                        logs = dict(zip(logs.keys(), vals / world))
+                    self.history.append({k: float(v) for k, v in logs.items()})
             if rank == 0 and self.root:
                 os.makedirs(self.root, exist_ok=True)
                 model.save_checkpoint(os.path.join(self.root, f"epoch={epoch}.ckpt"), opt, epoch + 1, step)
