@@ -31,18 +31,19 @@ def main(argv=None):
     if K < 2:
         raise SystemExit(f"out_channels ({hparams.out_channels}) must be >= len(loss_regression_weight) ({L}) + 2 classes")
     if hparams.gpu_sampler:                              # MedDataset(..., heatmap_group) of train_ldmks.py, volumes in HBM
-        from mednet_b200.sampler import GpuMedDataset
+        from mednet_b200.sampler import GpuMedDataset, IntensityAugmentation
         dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
 
-        def mk(n, seed):
+        def mk(n, seed, train=False):
             images, labels, hms = synthetic_cohort(n, hparams.gpu_sampler, hparams.in_channels, K, L, seed=seed)
             return GpuMedDataset(images, labels, hparams.patches_per_subject, hparams.patch_size, heatmaps=hms,
-                                 class_probabilities=hparams.class_probabilities, device=dev)
+                                 class_probabilities=hparams.class_probabilities if train else None, device=dev,
+                                 augmentation=IntensityAugmentation() if hparams.data_augmentation and train else None)
     else:
-        def mk(n, seed):
+        def mk(n, seed, train=False):
             return SyntheticSegmentationDataset(n, hparams.patch_size, hparams.in_channels, K, num_heatmaps=L, seed=seed)
     cls = LandmarkUNet3D if hparams.arch == "unet3d" else LandmarkNet
-    model = cls(hparams, training_dataset=mk(hparams.synthetic, hparams.seed),
+    model = cls(hparams, training_dataset=mk(hparams.synthetic, hparams.seed, True),
                 validation_dataset=mk(max(1, hparams.synthetic // 4), hparams.seed + 1))
     trainer = Trainer(gpus=hparams.gpus, max_epochs=hparams.max_epochs, default_root_dir=hparams.model_dir,
                       resume_from_checkpoint=hparams.resume, max_steps=hparams.max_steps)

@@ -27,14 +27,16 @@ def main(argv=None):
     logging.getLogger().setLevel(hparams.log_level)
     require_dataset(hparams, "train_seg")
     if hparams.gpu_sampler:                              # MedDataset(...) of train_seg.py:98-118, volumes in HBM
-        from mednet_b200.sampler import GpuMedDataset
+        from mednet_b200.sampler import GpuMedDataset, IntensityAugmentation
         dev = torch.device("cuda", int(__import__("os").environ.get("LOCAL_RANK", "0")))
 
-        def cohort(n, seed):
+        def cohort(n, seed, train):
             images, labels, _ = synthetic_cohort(n, hparams.gpu_sampler, hparams.in_channels, hparams.out_channels, seed=seed)
             return GpuMedDataset(images, labels, hparams.patches_per_subject, hparams.patch_size,
-                                 class_probabilities=hparams.class_probabilities, device=dev)
-        train_ds, val_ds = cohort(hparams.synthetic, hparams.seed), cohort(max(1, hparams.synthetic // 4), hparams.seed + 1)
+                                 class_probabilities=hparams.class_probabilities if train else None, device=dev,
+                                 augmentation=IntensityAugmentation() if hparams.data_augmentation and train else None)
+        train_ds = cohort(hparams.synthetic, hparams.seed, True)               # train_seg.py:98-106: transform on the
+        val_ds = cohort(max(1, hparams.synthetic // 4), hparams.seed + 1, False)  # training set only (:108-117)
     else:
         train_ds = SyntheticSegmentationDataset(hparams.synthetic, hparams.patch_size, hparams.in_channels,
                                                 hparams.out_channels, seed=hparams.seed)

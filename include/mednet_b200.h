@@ -426,6 +426,31 @@ typedef struct {
 int mednet_tile_scatter(const mednet_tile_scatter_params* p, mednet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Intensity augmentation of a sampled patch batch (opt-in, `--data_augmentation`).
+ * ref: examples/train_seg.py:82-86, train_ldmks.py:82-84 compose BrightnessTransform(mu=0, sigma=0.3),
+ * GammaTransform(gamma_range=(0.7, 1.3)), ContrastAugmentationTransform(contrast_range=(0.3, 1.7)) from the
+ * third-party package `batchgenerators` (requirements.txt:7, no version pinned; NOT vendored in the reference and
+ * not installed here -- the published algorithm is restated in oracle/augment.py, parity unpinned).
+ * The random decisions are drawn on the host and passed in `coef`, one row of 2 + 2C floats per sample:
+ *   [0]        gamma exponent, <= 0: no gamma step for this sample
+ *   [1]        1: apply the contrast step, 0: skip it
+ *   [2 .. 2+C) additive brightness offset per channel (0: none)
+ *   [2+C .. )  contrast factor per channel
+ * v = x + offset;  g = ((v - min v) / (range v + 1e-7)) ** gamma * range v + min v   (min / range over the SAMPLE);
+ * y = clip((g - mean_c g) * factor_c + mean_c g, min_c g, max_c g)                   (statistics per CHANNEL).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;         /* [B, V, C] fp32 patches, NDHWC (V = P0*P1*P2 voxels)                  */
+  void*        y;         /* [B, V, C] dst_dtype (MEDNET_F32 / MEDNET_BF16); must not overlap x   */
+  const float* coef;      /* [B, 2 + 2C] device array, see above                                  */
+  int64_t V;
+  int32_t B, C, dst_dtype;
+} mednet_intensity_aug_params;
+size_t mednet_intensity_augment_workspace_bytes(const mednet_intensity_aug_params* p);
+int mednet_intensity_augment(const mednet_intensity_aug_params* p, void* workspace, size_t workspace_bytes,
+                             mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * tcgen05 addressing calibration (see DESIGN.md "UMMA descriptor experiments").
  * The conv kernel reads its 27 taps as shifted windows of one TMA-written halo tile, i.e. with UMMA
  * descriptors whose start address is not aligned to the swizzle atom.  The probe runs D = A_window * I

@@ -78,7 +78,7 @@ def test_training_entry_points_with_the_gpu_resident_sampler(tmp_path):
     import train_ldmks
     import train_seg
     tr = train_seg.main(["--synthetic", "3", "--gpu_sampler", "48", "40", "36", "--class_probabilities", "0.3", "0.7",
-                         "--patches_per_subject", "2", "--patch_size", "32", "32", "32", "--batch_size", "2",
+                         "--patches_per_subject", "2", "--patch_size", "32", "32", "32", "--batch_size", "2", "--data_augmentation",
                          "--fmaps", "8", "--out_channels", "2", "--max_epochs", "1", "--model_dir", str(tmp_path / "s")])
     assert tr.history and all(np.isfinite(list(h.values())).all() for h in tr.history)
     tr = train_ldmks.main(["--synthetic", "2", "--gpu_sampler", "40", "40", "40", "--patches_per_subject", "2",

@@ -91,3 +91,64 @@ def test_sampler_feeds_training_step():
         opt.step()
         losses.append(float(out["loss"].detach()))
     assert len(losses) == 4 and all(np.isfinite(losses))
+
+
+@pytest.mark.parametrize("dtype,channels,size", [(torch.float32, 1, (16, 24, 8)), (torch.float32, 3, (20, 12, 28)),
+                                                  (torch.bfloat16, 2, (16, 16, 16)), (torch.float32, 1, (64, 64, 64))])
+def test_intensity_augmentation_matches_oracle_chain(dtype, channels, size):
+    """Device kernels vs the restated brightness -> gamma -> contrast chain (oracle/augment.py, parity unpinned: the
+    library itself is not available), same seed.  fp32 tolerance: 1e-5 of the value range (powf and the summation order
+    of the channel mean differ in the last bits); bf16 output: one rounding, 2^-8 relative."""
+    from oracle import augment as oaug
+    from mednet_b200 import ops
+    from mednet_b200.sampler import IntensityAugmentation
+    rs = np.random.RandomState(3)
+    B = 3
+    x = (rs.randn(B, channels, *size) * 1.5 + 0.5).astype(np.float32)
+    np.random.seed(7)
+    want = np.stack([oaug.augment_patch(x[b]) for b in range(B)])
+    aug = IntensityAugmentation(rng=np.random.RandomState(7))
+    coef = torch.as_tensor(np.stack([aug.draw(channels) for _ in range(B)])).cuda()
+    xd = torch.as_tensor(x).cuda().permute(0, 2, 3, 4, 1).contiguous()
+    y = ops.k_intensity_augment(xd, coef, dtype).permute(0, 4, 1, 2, 3).float().cpu().numpy()
+    span = float(want.max() - want.min())
+    if dtype == torch.float32:
+        assert np.abs(y - want).max() <= 1e-5 * span
+    else:
+        assert (np.abs(y - want) <= 2.0 ** -8 * np.abs(want) + 1e-5 * span).all()
+    # range preservation (contrast step): every channel stays inside the range it had after the gamma step
+    assert y.min() >= want.min() - 1e-5 * span and y.max() <= want.max() + 1e-5 * span
+    y2 = ops.k_intensity_augment(xd, coef, dtype).permute(0, 4, 1, 2, 3).float().cpu().numpy()
+    assert np.array_equal(y, y2)                                        # fixed-order partials: run-to-run identical
+
+
+def test_identity_coefficients_and_brightness_only_are_exact():
+    from mednet_b200 import ops
+    x = torch.randn(2, 8, 8, 8, 2, device="cuda")
+    coef = torch.tensor([[0, 0, 0, 0, 1, 1], [0, 0, 0.25, -0.5, 1, 1]], dtype=torch.float32, device="cuda")
+    y = ops.k_intensity_augment(x, coef, torch.float32)
+    assert torch.equal(y[0], x[0])
+    assert torch.equal(y[1], x[1] + torch.tensor([0.25, -0.5], device="cuda"))
+    with pytest.raises(Exception):
+        ops.k_intensity_augment(torch.randn(1, 4, 4, 4, 9, device="cuda"), torch.zeros(1, 20, device="cuda"), torch.float32)
+
+
+def test_sampler_with_augmentation_interleaves_draws_like_getitem():
+    """Position draws and augmentation draws share one generator, patch after patch (dataset.py:297-341): replaying the
+    oracle's position sampling + augmentation chain with the same seed reproduces the batch."""
+    from oracle import augment as oaug
+    from mednet_b200.sampler import GpuMedDataset, IntensityAugmentation
+    images, labels, _ = _cohort(5, False)
+    P, probs = [12, 16, 8], [0.3, 0.4, 0.3]
+    ds = GpuMedDataset(images, labels, 2, P, class_probabilities=probs, data_dtype=torch.float32,
+                       rng=np.random.RandomState(21), augmentation=IntensityAugmentation())
+    batch = ds.batch(range(4))
+    np.random.seed(21)
+    for b in range(4):
+        s = b % 3
+        ini, cls = osamp.sample_patch_position(labels[s][0], P, probs, osamp.label_any_maps(labels[s][0], 3))
+        assert np.array_equal(ini, batch["patch_position"][b]) and cls == batch["selected_class"][b]
+        crop, _ = osamp.crop_patch(images[s], labels[s], ini, P)
+        want = oaug.augment_patch(crop)
+        got = batch["data"][b].cpu().numpy()
+        assert np.abs(got - want).max() <= 1e-5 * float(want.max() - want.min())

@@ -77,3 +77,43 @@ def test_patch_as_large_as_the_volume_and_oversize():
     assert np.array_equal(ini, [0, 0, 0]) and np.array_equal(fin, [8, 8, 8])
     with pytest.raises(ValueError):
         PatchPositionSampler([torch.zeros((8, 8, 4), dtype=torch.uint8)], [8, 8, 8])
+
+
+def _apply_coefficients(x, row):
+    """NumPy evaluation of the coefficient contract in include/mednet_b200.h (mednet_intensity_aug_params)."""
+    C = x.shape[0]
+    v = x.astype(np.float32) + row[2:2 + C, None, None, None]
+    if row[0] > 0:
+        minm, rnge = v.min(), v.max() - v.min()
+        v = np.power((v - minm) / np.float32(rnge + np.float32(1e-7)), row[0]) * rnge + minm
+    if row[1]:
+        for c in range(C):
+            mn, lo, hi = v[c].mean(), v[c].min(), v[c].max()
+            v[c] = np.clip((v[c] - mn) * row[2 + C + c] + mn, lo, hi)
+    return v.astype(np.float32)
+
+
+@pytest.mark.parametrize("channels", [1, 3])
+def test_augmentation_draws_follow_the_oracle_chain(channels):
+    """Host-drawn coefficients + the documented formula == the restated library chain run with the same seed, patch after
+    patch (the draw count per patch is data independent, so the two generators stay in step)."""
+    from oracle import augment as oaug
+    from mednet_b200.sampler import IntensityAugmentation
+    rs = np.random.RandomState(1)
+    patches = [rs.randn(channels, 6, 7, 5).astype(np.float32) * 2 + 1 for _ in range(5)]
+    np.random.seed(42)
+    want = [oaug.augment_patch(p) for p in patches]
+    aug = IntensityAugmentation(rng=np.random.RandomState(42))
+    for p, w in zip(patches, want):
+        row = aug.draw(channels)
+        assert row.dtype == np.float32 and 0.7 <= row[0] <= 1.3 and row[1] == 1.0
+        assert ((row[2 + channels:] >= 0.3) & (row[2 + channels:] <= 1.7)).all()
+        np.testing.assert_allclose(_apply_coefficients(p, row), w, rtol=1e-5, atol=1e-5)
+
+
+def test_augmentation_can_be_switched_off_per_step():
+    from mednet_b200.sampler import IntensityAugmentation
+    row = IntensityAugmentation(p_per_sample=0.0, rng=np.random.RandomState(0)).draw(2)
+    assert row[0] == 0 and row[1] == 0 and (row[2:4] == 0).all()
+    x = np.random.RandomState(0).randn(2, 4, 4, 4).astype(np.float32)
+    assert np.array_equal(_apply_coefficients(x, row), x)

@@ -156,6 +156,25 @@ def k_channel_pad(x, c_dst):
     return out
 
 
+def k_intensity_augment(x, coef, dst_dtype):
+    """Brightness / gamma / contrast chain of the training scripts on a patch batch (include/mednet_b200.h).
+    x: (B, P0, P1, P2, C) fp32 NDHWC; coef: (B, 2 + 2C) fp32 device tensor of the host-drawn decisions."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or coef.dtype != torch.float32:
+        raise TypeError("mednet_b200: intensity augmentation takes fp32 patches and coefficients")
+    x, coef = _c(x), _c(coef)
+    b, c = x.shape[0], x.shape[-1]
+    if tuple(coef.shape) != (b, 2 + 2 * c):
+        raise ValueError(f"coef must be ({b}, {2 + 2 * c}), got {tuple(coef.shape)}")
+    y = torch.empty(x.shape, dtype=dst_dtype, device=x.device)
+    p = make("mednet_intensity_aug_params", x=_ptr(x), y=_ptr(y), coef=_ptr(coef), V=x.numel() // (b * c), B=b, C=c,
+             dst_dtype=_DT[dst_dtype])
+    ws = _ws(lib().mednet_intensity_augment_workspace_bytes(_abi.C.byref(p)), x.device)
+    check(lib().mednet_intensity_augment(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "intensity_augment")
+    _count(3)
+    return y
+
+
 # in_channels < 16 (the 1-channel image) can be zero-padded to 16 channels to run the first layer on the tensor-core
 # kernels (set to 16).  Measured on cfg-3 (profiles/r01j_first_layer_pad.txt): K = 16 leaves 2 MMAs per tap and issuer,
 # so the launches are latency-bound (2.3 ms each for fprop / dgrad, 1.9 ms wgrad) and the step is 1.1 ms SLOWER than with

@@ -62,6 +62,40 @@ def get_random_patch_indices(patch_size, img_shape, pos=None, rng=np.random):
     return index_ini, index_ini + patch_size
 
 
+class IntensityAugmentation:
+    """The chain ``--data_augmentation`` composes in the training scripts (examples/train_seg.py:82-86):
+    BrightnessTransform(mu, sigma) -> GammaTransform(gamma_range) -> ContrastAugmentationTransform(contrast_range), from
+    the third-party ``batchgenerators`` (not in this image; algorithm restated, see oracle/augment.py).  The random
+    decisions are drawn here on the host, one ``np.random`` call where the library makes one; the patch arithmetic runs
+    on the device (``mednet_intensity_augment``)."""
+
+    def __init__(self, mu=0.0, sigma=0.3, gamma_range=(0.7, 1.3), contrast_range=(0.3, 1.7), p_per_sample=1.0, rng=None):
+        self.mu, self.sigma, self.gamma_range, self.contrast_range = mu, sigma, tuple(gamma_range), tuple(contrast_range)
+        self.p_per_sample = p_per_sample
+        self.rng = np.random if rng is None else rng
+
+    def _around_one(self, rg):
+        if self.rng.random_sample() < 0.5 and rg[0] < 1:
+            return self.rng.uniform(rg[0], 1)
+        return self.rng.uniform(max(rg[0], 1), rg[1])
+
+    def draw(self, channels):
+        """-> float32 row [gamma | 0, contrast flag, C offsets, C factors] for one patch."""
+        row = np.zeros(2 + 2 * channels, dtype=np.float32)
+        row[2 + channels:] = 1.0
+        if self.rng.uniform() < self.p_per_sample:                       # brightness, per channel (p_per_channel = 1)
+            for c in range(channels):
+                if self.rng.uniform() <= 1.0:
+                    row[2 + c] = self.rng.normal(self.mu, self.sigma)
+        if self.rng.uniform() < self.p_per_sample:                       # gamma, one exponent per sample
+            row[0] = self._around_one(self.gamma_range)
+        if self.rng.uniform() < self.p_per_sample:                       # contrast, one factor per channel
+            row[1] = 1.0
+            for c in range(channels):
+                row[2 + channels + c] = self._around_one(self.contrast_range)
+        return row
+
+
 class PatchPositionSampler:
     """The host half of ``MedDataset.__getitem__`` (dataset.py:287-313): which subject, which class, where.  Works on
     class maps on any device (the tables are built with torch ops where the map lives and then kept on the host)."""
@@ -111,7 +145,7 @@ class GpuMedDataset:
     """
 
     def __init__(self, images, labels, samples_per_subject, patch_size, heatmaps=None, class_probabilities=None,
-                 subject_keys=None, transform=None, device="cuda", data_dtype=torch.bfloat16, rng=None):
+                 subject_keys=None, transform=None, device="cuda", data_dtype=torch.bfloat16, rng=None, augmentation=None):
         if not torch.cuda.is_available():
             raise RuntimeError("GpuMedDataset keeps volumes in GPU memory; no CUDA device is available")
         if len(images) != len(labels) or (heatmaps is not None and len(heatmaps) != len(images)):
@@ -122,6 +156,9 @@ class GpuMedDataset:
         self.transform = transform
         self.data_dtype = data_dtype
         self.rng = np.random if rng is None else rng
+        self.augmentation = augmentation                                 # IntensityAugmentation or None
+        if augmentation is not None and rng is not None:
+            augmentation.rng = self.rng                                  # one stream, interleaved as in __getitem__
         self.subject_keys = list(subject_keys) if subject_keys is not None else [str(i) for i in range(len(images))]
         self.images, self.labels, self.heatmaps = [], [], []
         for s, (img, lab) in enumerate(zip(images, labels)):
@@ -156,11 +193,16 @@ class GpuMedDataset:
         the compute dtype (the network consumes it as a view), 'label' (B, L+1, P0, P1, P2) uint8, plus the
         bookkeeping entries of dataset.py:332-334 as lists/arrays."""
         P = self.patch_size
-        drawn = [self.sample_position(int(i)) for i in indices]
-        B = len(drawn)
         C = self.images[0].shape[0]
         L = self.heatmaps[0].shape[0] if self.heatmaps else 0
-        data = torch.empty((B, P[0], P[1], P[2], C), dtype=self.data_dtype, device=self.device)
+        drawn, coef = [], []
+        for i in indices:                                                # per patch: position, then augmentation draws
+            drawn.append(self.sample_position(int(i)))                  # (dataset.py:297-341)
+            if self.augmentation is not None:
+                coef.append(self.augmentation.draw(C))
+        B = len(drawn)
+        stage_dtype = torch.float32 if self.augmentation is not None else self.data_dtype
+        data = torch.empty((B, P[0], P[1], P[2], C), dtype=stage_dtype, device=self.device)
         label = torch.empty((B, L + 1, P[0], P[1], P[2]), dtype=torch.uint8, device=self.device)
         origins = torch.as_tensor(np.stack([d[1] for d in drawn]).astype(np.int32)).to(self.device, non_blocking=True)
         for b, (subject, _, _) in enumerate(drawn):
@@ -169,6 +211,9 @@ class GpuMedDataset:
             if L:
                 self._gather(self.heatmaps[subject], label[b, :L], org, ncdhw=True)
             self._gather(self.labels[subject], label[b, L:], org, ncdhw=True)
+        if self.augmentation is not None:
+            coef_dev = torch.as_tensor(np.stack(coef)).to(self.device, non_blocking=True)
+            data = ops.k_intensity_augment(data, coef_dev, self.data_dtype)
         patch = {"subject_key": [self.subject_keys[d[0]] for d in drawn],
                  "patch_position": np.stack([d[1] for d in drawn]),
                  "selected_class": np.asarray([d[2] for d in drawn]),
