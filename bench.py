@@ -50,6 +50,10 @@ WORKLOADS = {
     "cfg4": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=4, edge=128, loss="DICE", predict=True,
                  volume=(512, 512, 400), overlap=16,
                  desc="sliding-window inference, 512x512x400 volume, 128^3 tiles, overlap 16 (180 tiles), tile batch 4"),
+    # the caller side of the training path (MedDataset.__getitem__ + augmentation): not the headline metric
+    "sampler": dict(sampler=True, subjects=4, volume=(320, 320, 256), batch=8, edge=128, probs=[0.3, 0.7],
+                    desc="random patch sampling from 4 HBM-resident subjects 320x320x256, batch 8 x 128^3 x 1 ch, "
+                         "class_probabilities [0.3, 0.7]"),
 }
 
 
@@ -238,6 +242,78 @@ def run_predict(args, wl):
         dist.destroy_process_group()
 
 
+def run_sampler(args, wl):
+    """--workload sampler: one "step" = one collated patch batch (positions drawn on the host in the reference's order,
+    crops [+ augmentation] on the device) ready for training_step.  value: plain sampling; config reports the augmented
+    variant; cpu_baseline: the reference's host procedure (oracle restatement, one DataLoader worker = one core) on the
+    same cohort, crop + casts + collate, without the pinned H2D copy a training step would add."""
+    import time
+    import numpy as np
+    from mednet_b200 import ops
+    from mednet_b200.sampler import GpuMedDataset, IntensityAugmentation
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    images, labels = [], []
+    for _ in range(wl["subjects"]):
+        img = torch.randn((1, *wl["volume"]), device=dev, generator=g)
+        lab = ((img[0] > 1.5) & (torch.rand(wl["volume"], device=dev, generator=g) > 0.5)).to(torch.uint8)
+        images.append(img)
+        labels.append(lab[None])
+    P, B = [wl["edge"]] * 3, wl["batch"]
+    vox = B * wl["edge"] ** 3
+    steps, warm = max(args.steps, 8), max(args.warmup, 3)
+    res = {}
+    for name, aug in (("plain", None), ("augmented", IntensityAugmentation())):
+        ds = GpuMedDataset(images, labels, 16, P, class_probabilities=wl["probs"], device=dev,
+                           rng=np.random.RandomState(1), augmentation=aug)
+        idx = np.arange(B)
+        for _ in range(warm):
+            ds.batch(idx)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            ds.batch(idx)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = dict(wall_ms=(time.perf_counter() - t0) * 1e3 / steps, dev_ms=e0.elapsed_time(e1) / steps,
+                         launches=(ops.launch_count - n0) // steps)
+    line = {"metric": "MedDataset patch sampling voxels/s", "value": vox / (res["plain"]["wall_ms"] * 1e-3), "unit": "voxels/s",
+            "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": res["plain"]["wall_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "sampler: " + wl["desc"], "timing": "host wall clock around batch() incl. the NumPy draws, "
+                       "synchronised at both ends", "device_ms_per_step": res["plain"]["dev_ms"],
+                       "augmented_ms_per_step": res["augmented"]["wall_ms"],
+                       "augmented_voxels_per_s": vox / (res["augmented"]["wall_ms"] * 1e-3),
+                       "augmented_launches": res["augmented"]["launches"], "l2": "source volumes (420 MB) larger than L2"},
+            "gpu_launches": res["plain"]["launches"] * steps}
+    if not args.no_cpu_baseline:
+        from oracle import augment as oaug                    # CPU baseline leg only (see module docstring)
+        from oracle import sampling as osamp
+        imgs_h, labs_h = [i.cpu().numpy() for i in images], [l.cpu().numpy() for l in labels]
+        maps = [osamp.label_any_maps(l[0], len(wl["probs"])) for l in labs_h]
+        cpu = {}
+        for name, aug in (("plain", False), ("augmented", True)):
+            np.random.seed(1)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                data, label = [], []
+                for i in range(B):
+                    s = i % wl["subjects"]
+                    ini, _ = osamp.sample_patch_position(labs_h[s][0], P, wl["probs"], maps[s])
+                    d, l = osamp.crop_patch(imgs_h[s], labs_h[s], ini, P)
+                    data.append(oaug.augment_patch(d) if aug else d)
+                    label.append(l)
+                np.stack(data), np.stack(label)
+            cpu[name] = vox * 2 / (time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": cpu["plain"], "unit": "voxels/s", "cores": 1, "kind": "port",
+                                "sample": "2 batches of 8 x 128^3 (position draws, crop, casts, collate); augmented: "
+                                          f"{cpu['augmented']:.4g} voxels/s"}
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -253,6 +329,11 @@ def main():
     wl = WORKLOADS[args.workload]
     if wl.get("predict"):
         run_predict(args, wl)
+        return
+    if wl.get("sampler"):
+        if args.impl == "reference":
+            raise SystemExit("the sampler workload has no separate reference arm: its line carries the host procedure as cpu_baseline")
+        run_sampler(args, wl)
         return
     if args.impl == "reference":
         run_reference_arm(args, wl)

@@ -191,6 +191,33 @@ __global__ void tile_gather_kernel(const TS* __restrict__ vol, TD* __restrict__ 
   }
 }
 
+// Row variant for channel-major tiles (ncdhw_out) and for C == 1, where an output row along axis 2 is one contiguous run
+// of the source volume: a warp per (tile, channel, x, y) row, lanes along z -- coalesced, one index decomposition per
+// row instead of five 64-bit divisions per element.
+template <typename TS, typename TD>
+__global__ void tile_gather_rows_kernel(const TS* __restrict__ vol, TD* __restrict__ tiles, const int32_t* __restrict__ org,
+                                        mednet_tile_gather_params p) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t rows = (int64_t)p.B * p.C * p.P0 * p.P1;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    int64_t t = r;
+    const int y = (int)(t % p.P1); t /= p.P1;
+    const int x = (int)(t % p.P0); t /= p.P0;
+    const int c = (int)(t % p.C);
+    const int b = (int)(t / p.C);
+    const int gx = org[b * 3 + 0] + x - p.O0, gy = org[b * 3 + 1] + y - p.O1, gz0 = org[b * 3 + 2] - p.O2;
+    const bool inside = gx >= 0 && gx < p.X && gy >= 0 && gy < p.Y;
+    const TS* src = vol + (((int64_t)c * p.X + (inside ? gx : 0)) * p.Y + (inside ? gy : 0)) * p.Z;
+    TD* dst = tiles + r * p.P2;
+    for (int z = lane; z < p.P2; z += 32) {
+      const int gz = gz0 + z;
+      float v = 0.f;
+      if (inside && gz >= 0 && gz < p.Z) v = to_f32<TS>(src[gz]);
+      dst[z] = from_f32<TD>(v);
+    }
+  }
+}
+
 __global__ void tile_scatter_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ vol,
                                     const int32_t* __restrict__ org, mednet_tile_scatter_params p) {
   const int c0 = p.P0 - 2 * p.O0, c1 = p.P1 - 2 * p.O1, c2 = p.P2 - 2 * p.O2;
@@ -304,21 +331,30 @@ extern "C" int mednet_landmark_extract(const mednet_landmark_params* p, void* wo
 extern "C" int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->volume && p->tiles && p->origins && p->B > 0 && p->C > 0, MEDNET_EINVAL);
   const int64_t total = (int64_t)p->B * p->C * p->P0 * p->P1 * p->P2;
-  const int nb = grid_for(total, 256);
+  const bool rows = p->ncdhw_out || p->C == 1;                 // for C == 1 the two tile layouts coincide
+  const int nb = rows ? grid_for((int64_t)p->B * p->C * p->P0 * p->P1 * 32, 256) : grid_for(total, 256);
+#define MEDNET_GATHER(TS, TD)                                                                                         \
+  do {                                                                                                                \
+    if (rows)                                                                                                         \
+      tile_gather_rows_kernel<TS, TD><<<nb, 256, 0, stream>>>((const TS*)p->volume, (TD*)p->tiles, p->origins, *p);   \
+    else                                                                                                              \
+      tile_gather_kernel<TS, TD><<<nb, 256, 0, stream>>>((const TS*)p->volume, (TD*)p->tiles, p->origins, *p);        \
+  } while (0)
   if (p->src_dtype == MEDNET_U8 && p->dst_dtype == MEDNET_U8) {
-    tile_gather_kernel<uint8_t, uint8_t><<<nb, 256, 0, stream>>>((const uint8_t*)p->volume, (uint8_t*)p->tiles, p->origins, *p);
+    MEDNET_GATHER(uint8_t, uint8_t);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   }
   MEDNET_REQUIRE(dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype), MEDNET_EUNSUPPORTED);
   if (p->src_dtype == MEDNET_F32 && p->dst_dtype == MEDNET_F32)
-    tile_gather_kernel<float, float><<<nb, 256, 0, stream>>>((const float*)p->volume, (float*)p->tiles, p->origins, *p);
+    MEDNET_GATHER(float, float);
   else if (p->src_dtype == MEDNET_F32)
-    tile_gather_kernel<float, bf16><<<nb, 256, 0, stream>>>((const float*)p->volume, (bf16*)p->tiles, p->origins, *p);
+    MEDNET_GATHER(float, bf16);
   else if (p->dst_dtype == MEDNET_F32)
-    tile_gather_kernel<bf16, float><<<nb, 256, 0, stream>>>((const bf16*)p->volume, (float*)p->tiles, p->origins, *p);
+    MEDNET_GATHER(bf16, float);
   else
-    tile_gather_kernel<bf16, bf16><<<nb, 256, 0, stream>>>((const bf16*)p->volume, (bf16*)p->tiles, p->origins, *p);
+    MEDNET_GATHER(bf16, bf16);
+#undef MEDNET_GATHER
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }
