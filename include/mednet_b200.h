@@ -417,6 +417,18 @@ typedef struct {
                              supported in addition to the float dtypes. */
 } mednet_tile_gather_params;
 int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_stream_t stream);
+/* Random-patch crop of a whole batch in one launch (ref mm/dataset.py:315-330 runs per sample on the host): every
+ * sample names its own source volume, so subjects of different shape share the launch.  No padding: patches lie inside
+ * their volume (get_random_patch_indices, dataset.py:54-88); voxels outside read as 0 all the same. */
+typedef struct {
+  const int64_t* table;   /* [B, 8] device array per sample: volume address ([C, X, Y, Z], src_dtype), X, Y, Z,
+                             origin0, origin1, origin2, 0                                                    */
+  void*          tiles;   /* ncdhw_out ? [B, C, P0,P1,P2] : [B, P0,P1,P2, C], dst_dtype                      */
+  int64_t tile_stride;    /* elements between consecutive samples in `tiles`; 0 = dense (C*P0*P1*P2).  Lets the
+                             heatmap and class-map crops land in their channel ranges of one label tensor   */
+  int32_t B, C, P0, P1, P2, src_dtype, dst_dtype, ncdhw_out;   /* dtypes: f32/bf16 -> f32/bf16, or u8 -> u8 */
+} mednet_patch_gather_params;
+int mednet_patch_gather(const mednet_patch_gather_params* p, mednet_stream_t stream);
 typedef struct {
   const uint8_t* tiles;   /* [B, Co, P0*P1*P2] epilogue output                                */
   uint8_t*       volume;  /* [Co, X, Y, Z]                                                     */

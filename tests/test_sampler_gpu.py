@@ -152,3 +152,23 @@ def test_sampler_with_augmentation_interleaves_draws_like_getitem():
         want = oaug.augment_patch(crop)
         got = batch["data"][b].cpu().numpy()
         assert np.abs(got - want).max() <= 1e-5 * float(want.max() - want.min())
+
+
+def test_tile_gather_channel_major_uint8_with_padding():
+    """mednet_tile_gather's channel-major / uint8 mode (one volume, padded coordinates) against a NumPy crop."""
+    from mednet_b200 import _abi, ops
+    from mednet_b200._abi import check, lib, make
+    rs = np.random.RandomState(4)
+    vol = rs.randint(0, 256, size=(3, 20, 17, 23)).astype(np.uint8)
+    P, O = (8, 6, 10), (2, 1, 3)
+    origins = np.array([[0, 0, 0], [12, 11, 13], [14, 12, 16]], dtype=np.int32)      # the last ones reach past the volume
+    vd = torch.as_tensor(vol).cuda()
+    od = torch.as_tensor(origins).cuda()
+    out = torch.empty((3, 3, *P), dtype=torch.uint8, device="cuda")
+    gp = make("mednet_tile_gather_params", volume=vd.data_ptr(), tiles=out.data_ptr(), origins=od.data_ptr(), B=3, C=3,
+              X=20, Y=17, Z=23, P0=P[0], P1=P[1], P2=P[2], O0=O[0], O1=O[1], O2=O[2], src_dtype=2, dst_dtype=2, ncdhw_out=1)
+    check(lib().mednet_tile_gather(_abi.C.byref(gp), ops._stream()), "tile_gather")
+    padded = np.pad(vol, [(0, 0)] + [(O[k], P[k]) for k in range(3)])
+    for b, o in enumerate(origins):
+        want = padded[:, o[0]:o[0] + P[0], o[1]:o[1] + P[1], o[2]:o[2] + P[2]]
+        assert np.array_equal(out[b].cpu().numpy(), want)

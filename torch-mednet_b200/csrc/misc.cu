@@ -218,6 +218,41 @@ __global__ void tile_gather_rows_kernel(const TS* __restrict__ vol, TD* __restri
   }
 }
 
+// Batch crop with a per-sample source table: a warp per (sample, channel, x, y) row, lanes along z.
+template <typename TS, typename TD>
+__global__ void patch_gather_kernel(const int64_t* __restrict__ table, TD* __restrict__ tiles, mednet_patch_gather_params p) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t rows = (int64_t)p.B * p.C * p.P0 * p.P1;
+  const int64_t stride = p.tile_stride ? p.tile_stride : (int64_t)p.C * p.P0 * p.P1 * p.P2;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    int64_t t = r;
+    const int y = (int)(t % p.P1); t /= p.P1;
+    const int x = (int)(t % p.P0); t /= p.P0;
+    const int c = (int)(t % p.C);
+    const int b = (int)(t / p.C);
+    const int64_t* e = table + (int64_t)b * 8;
+    const TS* vol = reinterpret_cast<const TS*>(e[0]);
+    const int X = (int)e[1], Y = (int)e[2], Z = (int)e[3];
+    const int gx = (int)e[4] + x, gy = (int)e[5] + y, gz0 = (int)e[6];
+    const bool inside = gx >= 0 && gx < X && gy >= 0 && gy < Y;
+    const TS* src = vol + (((int64_t)c * X + (inside ? gx : 0)) * Y + (inside ? gy : 0)) * Z;
+    TD* dst;
+    int zs;
+    TD* tile = tiles + (int64_t)b * stride;
+    if (p.ncdhw_out) {
+      dst = tile + (((int64_t)c * p.P0 + x) * p.P1 + y) * p.P2, zs = 1;
+    } else {
+      dst = tile + (((int64_t)x * p.P1 + y) * p.P2) * p.C + c, zs = p.C;
+    }
+    for (int z = lane; z < p.P2; z += 32) {
+      const int gz = gz0 + z;
+      float v = 0.f;
+      if (inside && gz >= 0 && gz < Z) v = to_f32<TS>(src[gz]);
+      dst[(int64_t)z * zs] = from_f32<TD>(v);
+    }
+  }
+}
+
 __global__ void tile_scatter_kernel(const uint8_t* __restrict__ tiles, uint8_t* __restrict__ vol,
                                     const int32_t* __restrict__ org, mednet_tile_scatter_params p) {
   const int c0 = p.P0 - 2 * p.O0, c1 = p.P1 - 2 * p.O1, c2 = p.P2 - 2 * p.O2;
@@ -355,6 +390,27 @@ extern "C" int mednet_tile_gather(const mednet_tile_gather_params* p, mednet_str
   else
     MEDNET_GATHER(bf16, bf16);
 #undef MEDNET_GATHER
+  MEDNET_LAUNCH_CHECK();
+  return MEDNET_OK;
+}
+
+extern "C" int mednet_patch_gather(const mednet_patch_gather_params* p, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->table && p->tiles && p->B > 0 && p->C > 0 && p->P0 > 0 && p->P1 > 0 && p->P2 > 0, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->tile_stride == 0 || p->tile_stride >= (int64_t)p->C * p->P0 * p->P1 * p->P2, MEDNET_EINVAL);
+  const int nb = grid_for((int64_t)p->B * p->C * p->P0 * p->P1 * 32, 256);
+  if (p->src_dtype == MEDNET_U8 && p->dst_dtype == MEDNET_U8)
+    patch_gather_kernel<uint8_t, uint8_t><<<nb, 256, 0, stream>>>(p->table, (uint8_t*)p->tiles, *p);
+  else {
+    MEDNET_REQUIRE(dtype_ok(p->src_dtype) && dtype_ok(p->dst_dtype), MEDNET_EUNSUPPORTED);
+    if (p->src_dtype == MEDNET_F32 && p->dst_dtype == MEDNET_F32)
+      patch_gather_kernel<float, float><<<nb, 256, 0, stream>>>(p->table, (float*)p->tiles, *p);
+    else if (p->src_dtype == MEDNET_F32)
+      patch_gather_kernel<float, bf16><<<nb, 256, 0, stream>>>(p->table, (bf16*)p->tiles, *p);
+    else if (p->dst_dtype == MEDNET_F32)
+      patch_gather_kernel<bf16, float><<<nb, 256, 0, stream>>>(p->table, (float*)p->tiles, *p);
+    else
+      patch_gather_kernel<bf16, bf16><<<nb, 256, 0, stream>>>(p->table, (bf16*)p->tiles, *p);
+  }
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }

@@ -13,8 +13,10 @@ What is different (B200-first):
   * volumes live on the device (fp32/bf16 images, uint8 labels/heatmaps; 180 GB of HBM holds whole cohorts);
   * the per-class candidate tables (``np.any(label == c, axis=2)`` + first index along axis 2) are built ONCE on the
     device at construction (dataset.py:268-279 builds only the any-maps and re-runs argwhere for every sample);
-  * the crop is one ``mednet_tile_gather`` launch per array and sample, writing straight into the batch tensor in the
-    network's layout (NDHWC, compute dtype) -- no float32 staging, no collate, no host<->device copy per step.
+  * the crop is one ``mednet_patch_gather`` launch per array (images, heatmaps, class map) for the WHOLE batch -- a
+    per-sample table names the source volume, so subjects of different shape share the launch -- writing straight into
+    the batch tensors in the network's layout (NDHWC, compute dtype; labels channel-major uint8): no float32 staging,
+    no collate, and per step only a (3, B, 8) int64 table going host -> device.
 
 Not covered: the HDF5/zarr readers (dataset.py:109-260; hand arrays in) and the batchgenerators augmentation chain
 (``transform``; pass a callable working on the device dict if needed).
@@ -172,6 +174,9 @@ class GpuMedDataset:
             self.labels.append(lab)
             if heatmaps is not None:
                 self.heatmaps.append(torch.as_tensor(heatmaps[s]).to(self.device, torch.uint8).contiguous())
+        for name, vols in (("images", self.images), ("heatmaps", self.heatmaps)):
+            if any(v.shape[0] != vols[0].shape[0] or v.dtype != vols[0].dtype for v in vols):
+                raise ValueError(f"{name}: every subject needs the same channel count and dtype (one crop launch per batch)")
         self.sample_position = PatchPositionSampler([l[0] for l in self.labels], self.patch_size, class_probabilities,
                                                     self.rng)
 
@@ -179,13 +184,13 @@ class GpuMedDataset:
         return len(self.images) * self.samples_per_subject          # dataset.py:281-283
 
     # ---- device side: crops -------------------------------------------------------------------------------------------
-    def _gather(self, vol, out, origin_dev, ncdhw):
-        c, X, Y, Z = vol.shape
+    def _gather(self, vols, table, out, tile_stride, ncdhw):
+        """One launch for the whole batch: ``table`` (B, 8) int64 on the device names each sample's source volume."""
         P = self.patch_size
-        gp = make("mednet_tile_gather_params", volume=vol.data_ptr(), tiles=out.data_ptr(), origins=origin_dev.data_ptr(),
-                  B=1, C=c, X=X, Y=Y, Z=Z, P0=P[0], P1=P[1], P2=P[2], O0=0, O1=0, O2=0,
-                  src_dtype=ops._dt(vol), dst_dtype=ops._dt(out), ncdhw_out=int(ncdhw))
-        check(lib().mednet_tile_gather(_abi.C.byref(gp), ops._stream()), "tile_gather")
+        gp = make("mednet_patch_gather_params", table=table.data_ptr(), tiles=out.data_ptr(), tile_stride=tile_stride,
+                  B=table.shape[0], C=vols[0].shape[0], P0=P[0], P1=P[1], P2=P[2], src_dtype=ops._dt(vols[0]),
+                  dst_dtype=ops._dt(out), ncdhw_out=int(ncdhw))
+        check(lib().mednet_patch_gather(_abi.C.byref(gp), ops._stream()), "patch_gather")
         ops._count()
 
     def batch(self, indices):
@@ -204,13 +209,19 @@ class GpuMedDataset:
         stage_dtype = torch.float32 if self.augmentation is not None else self.data_dtype
         data = torch.empty((B, P[0], P[1], P[2], C), dtype=stage_dtype, device=self.device)
         label = torch.empty((B, L + 1, P[0], P[1], P[2]), dtype=torch.uint8, device=self.device)
-        origins = torch.as_tensor(np.stack([d[1] for d in drawn]).astype(np.int32)).to(self.device, non_blocking=True)
-        for b, (subject, _, _) in enumerate(drawn):
-            org = origins[b:b + 1]
-            self._gather(self.images[subject], data[b], org, ncdhw=False)
-            if L:
-                self._gather(self.heatmaps[subject], label[b, :L], org, ncdhw=True)
-            self._gather(self.labels[subject], label[b, L:], org, ncdhw=True)
+        arrays = [self.images] + ([self.heatmaps] if L else []) + [self.labels]
+        table = np.zeros((len(arrays), B, 8), dtype=np.int64)           # one upload names every crop of the batch
+        for b, (subject, index_ini, _) in enumerate(drawn):
+            for a, vols in enumerate(arrays):
+                table[a, b, 0] = vols[subject].data_ptr()
+                table[a, b, 1:4] = vols[subject].shape[1:]
+                table[a, b, 4:7] = index_ini
+        table = torch.as_tensor(table).to(self.device, non_blocking=True)
+        self._gather(self.images, table[0], data, 0, ncdhw=False)
+        stride = label[0].numel()
+        if L:
+            self._gather(self.heatmaps, table[1], label, stride, ncdhw=True)
+        self._gather(self.labels, table[-1], label[:, L:], stride, ncdhw=True)
         if self.augmentation is not None:
             coef_dev = torch.as_tensor(np.stack(coef)).to(self.device, non_blocking=True)
             data = ops.k_intensity_augment(data, coef_dev, self.data_dtype)
