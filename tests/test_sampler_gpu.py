@@ -172,3 +172,30 @@ def test_tile_gather_channel_major_uint8_with_padding():
     for b, o in enumerate(origins):
         want = padded[:, o[0]:o[0] + P[0], o[1]:o[1] + P[1], o[2]:o[2] + P[2]]
         assert np.array_equal(out[b].cpu().numpy(), want)
+
+
+def test_reference_constructor_reads_groups_and_keeps_all_label_channels():
+    """MedDataset(data_path, subject_keys, ...) with the reference's argument order (dataset.py:211-222): groups come from a
+    reader, images are stored with the reference's float16 rounding, every label channel is cropped and the LAST one
+    drives the class-balanced positions (dataset.py:307, 319-321)."""
+    from mednet_b200.dataset import DataReaderArrays, MedDataset
+    rs = np.random.RandomState(8)
+    shapes = {"s1": (24, 20, 18), "s2": (20, 26, 22)}
+    store = {"images": {k: rs.randn(1, *s).astype(np.float32) for k, s in shapes.items()},
+             "labels": {k: np.stack([rs.randint(0, 2, s), (rs.rand(*s) > 0.9) * 1]).astype(np.uint8) for k, s in shapes.items()},
+             "heatmaps": {k: rs.randint(0, 256, (2,) + s).astype(np.uint8) for k, s in shapes.items()}}
+    P, probs = [8, 8, 8], [0.2, 0.8]
+    ds = MedDataset(store, ["s1", "s2"], 3, P, "images", "labels", "heatmaps", DataReaderArrays, probs,
+                    data_dtype=torch.float32, rng=np.random.RandomState(2))
+    assert len(ds) == 6
+    batch = ds.batch(range(4))
+    assert batch["label"].shape == (4, 2 + 2, *P) and batch["subject_key"] == ["s1", "s2", "s1", "s2"]
+    np.random.seed(2)
+    for b, key in enumerate(batch["subject_key"]):
+        cmap = store["labels"][key][-1]
+        ini, cls = osamp.sample_patch_position(cmap, P, probs, osamp.label_any_maps(cmap, 2))
+        assert np.array_equal(ini, batch["patch_position"][b]) and cls == batch["selected_class"][b]
+        full = np.concatenate([store["heatmaps"][key], store["labels"][key]], axis=0)
+        want_d, want_l = osamp.crop_patch(store["images"][key].astype(np.float16), full, ini, P)
+        assert np.array_equal(batch["data"][b].cpu().numpy(), want_d)
+        assert np.array_equal(batch["label"][b].cpu().numpy(), want_l)

@@ -117,3 +117,25 @@ def test_augmentation_can_be_switched_off_per_step():
     assert row[0] == 0 and row[1] == 0 and (row[2:4] == 0).all()
     x = np.random.RandomState(0).randn(2, 4, 4, 4).astype(np.float32)
     assert np.array_equal(_apply_coefficients(x, row), x)
+
+
+def test_reader_adapters_follow_the_reference_interface(tmp_path):
+    """DataReader surface of dataset.py:109-207: storage dtypes on preload, lazy handles otherwise, a clear error for the
+    container formats whose libraries are not installed."""
+    from mednet_b200.dataset import DataReaderArrays, DataReaderHDF5, one_hot_to_label
+    arrays = {"images/a": np.ones((1, 4, 5, 6), np.float32) * 1.0009765625, "labels/a": np.full((1, 4, 5, 6), 3, np.int64)}
+    path = tmp_path / "cohort.npz"
+    np.savez(path, **arrays)
+    r = DataReaderArrays(str(path))
+    img = r.read_data_to_memory(["a"], "images", dtype=np.float16)[0]
+    lab = r.read_data_to_memory(["a"], "labels", dtype=np.uint8)[0]
+    assert img.dtype == np.float16 and lab.dtype == np.uint8 and float(img.flat[0]) == 1.0009765625 and lab.max() == 3
+    assert r.get_data_shape(["a"], "labels") == {"a": (1, 4, 5, 6)}
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            DataReaderHDF5(str(path))
+    one_hot = np.zeros((2, 1, 1, 3))
+    one_hot[0, 0, 0, 1] = one_hot[1, 0, 0, 2] = 1
+    assert one_hot_to_label(one_hot).tolist() == [[[[0, 1, 2]]]]

@@ -6,7 +6,7 @@ Drop-in surface (same names as the reference package ``midasmednet``):
     from mednet_b200.unet.loss import DiceLoss, dice_metric
     from mednet_b200.segmentation import SegmentationNet
     from mednet_b200.landmarks import LandmarkNet
-    from mednet_b200.dataset import grid_patch_generator
+    from mednet_b200.dataset import grid_patch_generator, MedDataset, DataReaderHDF5   # reference constructor / readers
     from mednet_b200.sampler import GpuMedDataset          # MedDataset's random patches from HBM-resident volumes
 
 ``install_as_midasmednet()`` registers these modules under the reference's import paths so that unmodified

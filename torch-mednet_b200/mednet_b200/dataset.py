@@ -71,3 +71,106 @@ class SyntheticSegmentationDataset(Dataset):
         else:
             label = cls
         return {"data": data, "label": label}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Reference-facing dataset surface (midasmednet/dataset.py:90-283): readers + MedDataset with the same constructor.
+# The readers are thin adapters over the storage libraries (imported lazily; neither h5py nor zarr is part of this
+# image) -- the work is in ``sampler.GpuMedDataset``, which keeps what they return in GPU memory.
+# ------------------------------------------------------------------------------------------------------------------
+def one_hot_to_label(data, add_background=True):
+    """(C,H,W,D) one-hot -> (1,H,W,D) class values (dataset.py:90-107)."""
+    data = np.asarray(data)
+    if add_background:
+        data = np.concatenate([~np.any(data, axis=0, keepdims=True), data], axis=0)
+    return np.argmax(data, axis=0)[None]
+
+
+class DataReader:
+    """Reader interface of the reference (dataset.py:109-150): ``read`` yields one array per subject key."""
+
+    def read(self, subject_keys, group, dtype=np.float16, preload=True):
+        raise NotImplementedError
+
+    def read_data_to_memory(self, subject_keys, group, dtype=np.float16, preload=True):
+        return list(self.read(subject_keys, group, dtype, preload))
+
+    def get_data_shape(self, subject_keys, group):
+        return {k: tuple(np.shape(d)) for k, d in zip(subject_keys, self.read(subject_keys, group, None, False))}
+
+    def close(self):
+        pass
+
+
+class DataReaderArrays(DataReader):
+    """In-memory store ``{group: {key: array}}`` (or an ``.npz`` file with ``group/key`` entries)."""
+
+    def __init__(self, path_data):
+        if isinstance(path_data, (str, bytes)) or hasattr(path_data, "__fspath__"):
+            npz = np.load(path_data)
+            store = {}
+            for name in npz.files:
+                group, key = name.split("/", 1)
+                store.setdefault(group, {})[key] = npz[name]
+            path_data = store
+        self.store = path_data
+
+    def read(self, subject_keys, group, dtype=np.float16, preload=True):
+        for k in subject_keys:
+            data = self.store[group][k]
+            yield np.asarray(data).astype(dtype) if (preload and dtype is not None) else data
+
+
+class _HierarchicalReader(DataReader):
+    """``<file>/<group>/<key>`` datasets of an HDF5 or zarr container (dataset.py:152-207)."""
+    module = opener = None
+
+    def __init__(self, path_data):
+        try:
+            lib = __import__(self.module)
+        except ImportError as e:
+            raise ImportError(f"{type(self).__name__} needs the '{self.module}' package, which is not installed; "
+                              "use DataReaderArrays or pass your own DataReader subclass as ReaderClass") from e
+        self.path_data = path_data
+        self.root = getattr(lib, self.opener)(str(path_data), "r")
+
+    def read(self, subject_keys, group, dtype=np.float16, preload=True):
+        for k in subject_keys:
+            data = self.root[f"{group}/{k}"]
+            yield data[:].astype(dtype) if (preload and dtype is not None) else data
+
+    def get_data_attribute(self, subject_keys, group, attribute):
+        return {k: self.root[f"{group}/{k}"].attrs[attribute] for k in subject_keys}
+
+    def close(self):
+        if hasattr(self.root, "close"):
+            self.root.close()
+
+
+class DataReaderHDF5(_HierarchicalReader):
+    module, opener = "h5py", "File"
+
+
+class DataReaderZarr(_HierarchicalReader):
+    module, opener = "zarr", "open"
+
+
+def MedDataset(data_path, subject_keys, samples_per_subject, patch_size, image_group='images', label_group='labels',
+               heatmap_group=None, ReaderClass=DataReaderHDF5, class_probabilities=None, preload=True, transform=None,
+               **device_options):
+    """The reference's constructor (dataset.py:211-260) returning the device-resident dataset: the groups are read once
+    through ``ReaderClass`` with the reference's storage dtypes (images float16, labels / heatmaps uint8), moved to GPU
+    memory and sampled there (``sampler.GpuMedDataset``; ``preload`` is implied).  ``transform``: an
+    ``IntensityAugmentation`` runs as CUDA kernels; any other callable receives the batch dict of device tensors."""
+    from .sampler import GpuMedDataset, IntensityAugmentation
+    reader = ReaderClass(data_path)
+    images = reader.read_data_to_memory(subject_keys, image_group, dtype=np.float16, preload=True)
+    labels = reader.read_data_to_memory(subject_keys, label_group, dtype=np.uint8, preload=True)
+    heatmaps = reader.read_data_to_memory(subject_keys, heatmap_group, dtype=np.uint8, preload=True) if heatmap_group else None
+    reader.close()
+    assert len(images) == len(labels)                                      # dataset.py:263
+    augmentation = transform if isinstance(transform, IntensityAugmentation) else None
+    return GpuMedDataset([np.asarray(i, dtype=np.float32) for i in images], list(labels),
+                         samples_per_subject, patch_size, heatmaps=heatmaps, class_probabilities=class_probabilities,
+                         subject_keys=subject_keys, transform=None if augmentation is not None else transform,
+                         augmentation=augmentation, **device_options)

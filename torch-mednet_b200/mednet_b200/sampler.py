@@ -142,7 +142,7 @@ class GpuMedDataset:
     """``MedDataset(...)[idx]`` semantics on device-resident arrays.
 
     images:  list of (C, X, Y, Z) arrays/tensors (any float dtype; stored fp32 unless already bf16)
-    labels:  list of (1, X, Y, Z) or (X, Y, Z) integer class maps
+    labels:  list of (Cl, X, Y, Z) or (X, Y, Z) integer label arrays; the class map is the LAST channel (dataset.py:307)
     heatmaps: optional list of (L, X, Y, Z) arrays (stored and emitted as uint8, dataset.py:324-327)
     """
 
@@ -167,17 +167,17 @@ class GpuMedDataset:
             img = torch.as_tensor(img)
             img = img.to(self.device, torch.bfloat16 if img.dtype == torch.bfloat16 else torch.float32).contiguous()
             lab = torch.as_tensor(lab)
-            lab = lab.reshape((1,) + tuple(lab.shape[-3:])).to(self.device, torch.uint8).contiguous()
+            lab = lab.reshape((-1,) + tuple(lab.shape[-3:])).to(self.device, torch.uint8).contiguous()
             if img.dim() != 4 or tuple(img.shape[1:]) != tuple(lab.shape[1:]):
                 raise ValueError(f"subject {s}: image {tuple(img.shape)} and label {tuple(lab.shape)} do not match")
             self.images.append(img)
             self.labels.append(lab)
             if heatmaps is not None:
                 self.heatmaps.append(torch.as_tensor(heatmaps[s]).to(self.device, torch.uint8).contiguous())
-        for name, vols in (("images", self.images), ("heatmaps", self.heatmaps)):
+        for name, vols in (("images", self.images), ("labels", self.labels), ("heatmaps", self.heatmaps)):
             if any(v.shape[0] != vols[0].shape[0] or v.dtype != vols[0].dtype for v in vols):
                 raise ValueError(f"{name}: every subject needs the same channel count and dtype (one crop launch per batch)")
-        self.sample_position = PatchPositionSampler([l[0] for l in self.labels], self.patch_size, class_probabilities,
+        self.sample_position = PatchPositionSampler([l[-1] for l in self.labels], self.patch_size, class_probabilities,
                                                     self.rng)
 
     def __len__(self):
@@ -195,7 +195,7 @@ class GpuMedDataset:
 
     def batch(self, indices):
         """Samples ``len(indices)`` patches and returns the collated dict: 'data' (B, C, P0, P1, P2) in NDHWC memory and
-        the compute dtype (the network consumes it as a view), 'label' (B, L+1, P0, P1, P2) uint8, plus the
+        the compute dtype (the network consumes it as a view), 'label' (B, L+Cl, P0, P1, P2) uint8, plus the
         bookkeeping entries of dataset.py:332-334 as lists/arrays."""
         P = self.patch_size
         C = self.images[0].shape[0]
@@ -208,7 +208,7 @@ class GpuMedDataset:
         B = len(drawn)
         stage_dtype = torch.float32 if self.augmentation is not None else self.data_dtype
         data = torch.empty((B, P[0], P[1], P[2], C), dtype=stage_dtype, device=self.device)
-        label = torch.empty((B, L + 1, P[0], P[1], P[2]), dtype=torch.uint8, device=self.device)
+        label = torch.empty((B, L + self.labels[0].shape[0], P[0], P[1], P[2]), dtype=torch.uint8, device=self.device)
         arrays = [self.images] + ([self.heatmaps] if L else []) + [self.labels]
         table = np.zeros((len(arrays), B, 8), dtype=np.int64)           # one upload names every crop of the batch
         for b, (subject, index_ini, _) in enumerate(drawn):
