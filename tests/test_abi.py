@@ -66,3 +66,14 @@ def test_missing_extension_fails_loudly(monkeypatch):
     monkeypatch.setattr(_abi, "LIB_PATH", os.path.join(os.path.dirname(_abi.LIB_PATH), "does_not_exist.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _abi.lib()
+
+
+def test_every_entry_point_is_documented_for_integrators():
+    """INTEGRATION.md maps each launcher of include/mednet_b200.h to the reference call site it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "mednet_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set(re.findall(r"\b(mednet_[a-z0-9_]+)\s*\(", header))
+    missing = sorted(n for n in names if not n.endswith("_workspace_bytes") and n not in doc)
+    assert not missing, missing
