@@ -50,6 +50,16 @@ WORKLOADS = {
     "cfg4": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=4, edge=128, loss="DICE", predict=True,
                  volume=(512, 512, 400), overlap=16,
                  desc="sliding-window inference, 512x512x400 volume, 128^3 tiles, overlap 16 (180 tiles), tile batch 4"),
+    # further variants SURVEY.md section 8(d) lists for the same configurations (same code paths, other parameters)
+    "cfg3_ce": dict(arch="unet3d", f_maps=64, classes=4, heatmaps=0, batch=8, edge=128, loss="CE",
+                    desc="cfg-3 with the weighted cross-entropy loss instead of Dice"),
+    "cfg2_res": dict(arch="residual", f_maps=64, classes=2, heatmaps=8, batch=4, edge=96, loss="DICE",
+                     desc="cfg-2 on LandmarkNet as shipped: ResidualUNet3D f=64 5-level, 8 heatmaps + 2 classes, batch 4, 96^3"),
+    "cfg5_res": dict(arch="residual", f_maps=32, classes=2, heatmaps=0, batch=2, edge=160, loss="DICE",
+                     desc="cfg-5 on ResidualUNet3D(1,2) f=32 5-level, batch 2 per GPU, 160^3, Dice"),
+    "cfg4_o32": dict(arch="unet3d", f_maps=64, classes=2, heatmaps=0, batch=4, edge=128, loss="DICE", predict=True,
+                     volume=(512, 512, 400), overlap=32,
+                     desc="sliding-window inference, 512x512x400 volume, 128^3 tiles, overlap 32 (448 tiles), tile batch 4"),
     # the caller side of the training path (MedDataset.__getitem__ + augmentation): not the headline metric
     "sampler": dict(sampler=True, subjects=4, volume=(320, 320, 256), batch=8, edge=128, probs=[0.3, 0.7],
                     desc="random patch sampling from 4 HBM-resident subjects 320x320x256, batch 8 x 128^3 x 1 ch, "
