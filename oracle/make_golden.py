@@ -164,6 +164,28 @@ def golden_sampling():
                         index_ini=np.array(ini), selected_class=np.array(cls))
 
 
+def golden_loss_variants(rloss):
+    """Loss configurations the small-net fixtures do not reach: sigmoid normalisation, unweighted Dice, unweighted CE, a
+    class that never occurs, the fp32 one-hot -- values and d(loss)/d(logits) from the reference's own classes."""
+    torch.manual_seed(99)
+    logits = (2.0 * torch.randn(2, 3, 6, 5, 4)).requires_grad_(True)
+    labels = torch.randint(0, 2, (2, 6, 5, 4))                   # class 2 never occurs
+    w = torch.tensor([0.2, 1.0, 0.5])
+    cases = {"dice_softmax_unweighted": rloss.DiceLoss(), "dice_softmax_weighted": rloss.DiceLoss(weight=w),
+             "dice_sigmoid_unweighted": rloss.DiceLoss(sigmoid_normalization=True),
+             "dice_sigmoid_weighted": rloss.DiceLoss(weight=w, sigmoid_normalization=True),
+             "ce_unweighted": torch.nn.CrossEntropyLoss(), "ce_weighted": torch.nn.CrossEntropyLoss(weight=w)}
+    out = {"logits": logits.detach().numpy(), "labels": labels.numpy(), "weight": w.numpy(),
+           "one_hot": rloss.expand_as_one_hot(labels, 3).numpy(),
+           "dice_metric": rloss.dice_metric(logits.detach(), labels).numpy()}
+    for name, fn in cases.items():
+        value = fn(logits, labels)
+        grad, = torch.autograd.grad(value, logits)
+        out[name] = value.detach().numpy()
+        out[name + ".dlogits"] = grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "loss_variants.npz"), **out)
+
+
 def golden_semantics():
     """KATs probed by the survey (last row), recorded from live torch."""
     import torch.nn.functional as F
@@ -194,6 +216,7 @@ def main():
     golden_tiling()
     golden_semantics()
     golden_sampling()
+    golden_loss_variants(rloss)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/make_golden.py from {REF} with torch {torch.__version__}, numpy {np.__version__}\n")
     print("golden vectors written to", os.path.abspath(OUT))

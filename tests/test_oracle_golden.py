@@ -219,3 +219,25 @@ def test_bf16_storage_results_are_defined_only_up_to_summation_order_noise():
     fmt = rel(base, ref32)
     assert 1e-3 < moved < fmt            # fp32-ulp noise moves the bf16 result by 0.1..1 %, still less than the format costs
     assert 1e-2 < fmt < 1e-1
+
+
+def test_loss_variants_match_reference_classes(golden):
+    """Sigmoid normalisation, unweighted Dice / CE, an absent class and the fp32 one-hot: values and d(loss)/d(logits)
+    of the oracle against the reference's own DiceLoss / nn.CrossEntropyLoss (tests/golden/loss_variants.npz)."""
+    from oracle import loss as oloss
+    g = golden("loss_variants")
+    labels, w = torch.from_numpy(g["labels"]), torch.from_numpy(g["weight"])
+    assert np.array_equal(oloss.one_hot(labels, 3).numpy(), g["one_hot"])
+    np.testing.assert_allclose(oloss.dice_metric(torch.from_numpy(g["logits"]), labels).numpy(), g["dice_metric"], rtol=1e-6)
+    cases = {"dice_softmax_unweighted": lambda z: oloss.dice_loss(z, labels),
+             "dice_softmax_weighted": lambda z: oloss.dice_loss(z, labels, weight=w),
+             "dice_sigmoid_unweighted": lambda z: oloss.dice_loss(z, labels, sigmoid_normalization=True),
+             "dice_sigmoid_weighted": lambda z: oloss.dice_loss(z, labels, weight=w, sigmoid_normalization=True),
+             "ce_unweighted": lambda z: oloss.weighted_cross_entropy(z, labels),
+             "ce_weighted": lambda z: oloss.weighted_cross_entropy(z, labels, w)}
+    for name, fn in cases.items():
+        z = torch.from_numpy(g["logits"]).clone().requires_grad_(True)
+        value = fn(z)
+        grad, = torch.autograd.grad(value, z)
+        np.testing.assert_allclose(value.detach().numpy(), g[name], rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(grad.numpy(), g[name + ".dlogits"], rtol=1e-5, atol=1e-9, err_msg=name)
