@@ -29,7 +29,7 @@ class _TaskMixin:
     def train_dataloader(self):
         """segmentation.py:122-127; under torch.distributed every rank gets its own share of the epoch."""
         return sharded_loader(self.training_dataset, self.batch_size, self.num_workers, shuffle=True,
-                              epoch=getattr(self, "current_epoch", 0))
+                              epoch=getattr(self, "current_epoch", 0), seed=getattr(getattr(self, "hparams", None), "seed", 0) or 0)
 
     def val_dataloader(self):
         return sharded_loader(self.validation_dataset, self.batch_size, self.num_workers, shuffle=False)
