@@ -105,8 +105,14 @@ def hparams_for(wl):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_voxels_per_s(wl, steps, warmup, edge=None, batch=None):
-    """Times the oracle port (forward + loss + backward + Adam) on the host cores; returns (voxels/s, info)."""
+def cpu_oracle_voxels_per_s(wl, steps, warmup, edge=None, batch=None, forward_only=False):
+    """Times the reference's CPU path (forward + loss + backward + Adam, or forward only for the predict workloads) on the
+    host cores; returns (voxels/s, info).  kind "reference": the reference's own modules (oracle/_ref, vendored unmodified
+    by oracle/build_ref.py) driven by the step of segmentation.py:58-65 / landmarks.py:66-83; kind "port": the oracle
+    restatement when oracle/_ref is absent."""
+    import time
+    from oracle import build_ref
+    from oracle import loss as oloss
     from oracle import steps as osteps
     from oracle import unet as ounet
     torch.set_num_threads(os.cpu_count() or 1)
@@ -115,36 +121,96 @@ def cpu_oracle_voxels_per_s(wl, steps, warmup, edge=None, batch=None):
     sub = dict(wl, edge=edge, batch=batch)
     out_ch = wl["classes"] + wl["heatmaps"]
     kind = "residual" if wl["arch"] == "residual" else "unet3d"
-    sd = (ounet.make_residual_unet3d_state_dict if kind == "residual" else ounet.make_unet3d_state_dict)(1, out_ch, wl["f_maps"])
     b = synthetic_batch(sub, 0, "cpu")
-    kw = dict(f_maps=wl["f_maps"])
-    if wl["heatmaps"]:
-        hp = hparams_for(wl)
-        times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="ldmk",
-                                              loss_class=hp.loss_class, loss_class_weight=hp.loss_class_weight,
-                                              loss_regression_weight=hp.loss_regression_weight, **kw)
+    hp = hparams_for(wl)
+    ref = build_ref.load()
+    if ref is not None:
+        rmodel, rloss = ref
+        torch.manual_seed(0)
+        net = (rmodel.ResidualUNet3D if kind == "residual" else rmodel.UNet3D)(1, out_ch, False, f_maps=wl["f_maps"])
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)                     # segmentation.py:119-120
+        if wl["heatmaps"]:
+            cw = torch.tensor(hp.loss_class_weight)
+            rw = list(hp.loss_regression_weight)
+            L = wl["heatmaps"]
+            class_loss = rloss.DiceLoss(weight=cw) if hp.loss_class == "DICE" else torch.nn.CrossEntropyLoss(weight=cw)
+        else:
+            w = torch.tensor(hp.loss_weight)
+            crit = rloss.DiceLoss(weight=w) if hp.loss == "DICE" else torch.nn.CrossEntropyLoss(weight=w)   # segmentation.py:43-49
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            inputs = b["data"].float()
+            if forward_only:
+                with torch.no_grad():
+                    net(inputs)
+            else:
+                opt.zero_grad()
+                out = net(inputs)
+                labels = b["label"][:, -1].long()
+                if wl["heatmaps"]:                                             # landmarks.py:66-83, 125-134
+                    hm = b["label"][:, :-1].float()
+                    value = class_loss(out[:, L:], labels)
+                    for c in range(L):
+                        value = value + rw[c] * torch.nn.functional.mse_loss(out[:, c], hm[:, c])
+                else:
+                    value = crit(out, labels)
+                value.backward()
+                opt.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        impl = "the reference's own midasmednet.unet modules (oracle/_ref)"
+        k = "reference"
     else:
-        hp = hparams_for(wl)
-        times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="seg", loss=hp.loss,
-                                              loss_weight=hp.loss_weight, **kw)
+        sd = (ounet.make_residual_unet3d_state_dict if kind == "residual" else ounet.make_unet3d_state_dict)(1, out_ch, wl["f_maps"])
+        kw = dict(f_maps=wl["f_maps"])
+        if forward_only:
+            times = []
+            fwd = ounet.residual_unet3d_forward if kind == "residual" else ounet.unet3d_forward
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    fwd(sd, b["data"].float(), **kw)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+        elif wl["heatmaps"]:
+            times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="ldmk",
+                                                  loss_class=hp.loss_class, loss_class_weight=hp.loss_class_weight,
+                                                  loss_regression_weight=hp.loss_regression_weight, **kw)
+        else:
+            times, _ = osteps.time_training_steps(kind, sd, b, steps=steps, warmup=warmup, task="seg", loss=hp.loss,
+                                                  loss_weight=hp.loss_weight, **kw)
+        impl = "oracle port of the reference"
+        k = "port"
     t = sum(times) / len(times)
     vox = batch * edge ** 3
-    return vox / t, dict(seconds_per_step=t, sample=f"batch {batch} x {edge}^3 patch, {len(times)} timed step(s) after "
-                                                     f"{warmup} warm-up, fwd+loss+bwd+Adam, oracle port of the reference "
-                                                     f"(plain PyTorch fp32, {torch.get_num_threads()} threads)")
+    what = "forward" if forward_only else "fwd+loss+bwd+Adam"
+    return vox / t, dict(seconds_per_step=t, kind=k, edge=edge, batch=batch,
+                         sample=f"batch {batch} x {edge}^3 patch, {len(times)} timed step(s) after {warmup} warm-up, {what}, "
+                                f"{impl} (plain PyTorch fp32, {torch.get_num_threads()} threads)")
 
 
 def run_reference_arm(args, wl):
+    """The reference's CPU implementation of the path on this box's host cores, on the workload's own patch edge with a
+    batch of one (reduced N, voxels/s normalisation) so that K steps end within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    edge = min(wl["edge"], 64)
-    v, info = cpu_oracle_voxels_per_s(wl, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)), edge=edge, batch=1)
-    line = {"impl": "reference", "metric": "UNet3D train voxels/s", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
+    predict = bool(wl.get("predict"))
+    v, info = cpu_oracle_voxels_per_s(wl, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)), edge=wl["edge"],
+                                      batch=1, forward_only=predict)
+    metric = "UNet3D train voxels/s"
+    if predict:            # useful voxels of a tile = its centre crop (dataset.py:452-474)
+        v *= ((wl["edge"] - 2 * wl["overlap"]) / wl["edge"]) ** 3
+        metric = "UNet3D predict voxels/s"
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "l2": "inputs larger than L2"},
-            "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+            "higher_is_better": True, "scaling": "strong" if predict else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "per_step_sample": f"batch 1 x {wl['edge']}^3 (same patch "
+                       "edge and network as the GPU arm, batch reduced to 1; voxels/s normalised)",
+                       "l2": "inputs larger than L2"},
+            "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": info["kind"],
                              "sample": info["sample"]},
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -231,10 +297,19 @@ def run_predict(args, wl):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    from mednet_b200 import ops
     steps, warm = max(1, min(args.steps, 3)), 1
     for _ in range(warm):
         pred(vol_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.conv_events = []
+    launches0 = ops.launch_count
     ms = timed(lambda: pred(vol_dev), steps)
+    launches = ops.launch_count - launches0
+    conv_events, ops.conv_events = ops.conv_events, None
+    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(lambda: pred(vol_host).cpu(), steps)        # host volume in, stitched uint8 volume back on the host
     if rank == 0:
         useful = X * Y * Z
@@ -243,13 +318,44 @@ def run_predict(args, wl):
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload + ": " + wl["desc"], "tiles": tiles,
                            "computed_voxels_per_s": tiles * wl["edge"] ** 3 * steps / (ms * 1e-3),
+                           "sharding": f"tiles round-robin over {world} rank(s), no data-path collective; disjoint uint8 "
+                                       "regions combined once per volume (all_gather of per-rank tile outputs)",
                            "l2": "inputs larger than L2"},
+                "clocks": clocks,
                 "e2e": {"value": useful * steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                         "h2d_bytes_per_step": vol_host.numel() * 2, "d2h_bytes_per_step": (wl["heatmaps"] + 1) * useful,
-                        "ms_per_step": ms_e2e / steps}}
+                        "ms_per_step": ms_e2e / steps},
+                "gpu_launches": launches, "roofline": conv_roofline(conv_events, ms, None, None)}
+        if not args.no_cpu_baseline and world == 1:
+            v, info = cpu_oracle_voxels_per_s(wl, steps=2, warmup=1, edge=wl["edge"], batch=1, forward_only=True)
+            v *= ((wl["edge"] - 2 * wl["overlap"]) / wl["edge"]) ** 3      # useful voxels of a tile = its centre crop
+            line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": info["kind"],
+                                    "sample": info["sample"] + "; useful (centre-crop) voxels of the tile counted"}
+        else:
+            line["cpu_baseline"] = None
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_roofline(conv_events, ms_total, traffic, traffic_src):
+    """roofline object for the dominant kernel (tcgen05 implicit-GEMM conv, fprop [+ dgrad]) from its per-launch CUDA
+    events inside the timed region."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else \
+        "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    tc_flops = sum(f for f, _, _ in conv_events)
+    tc_ms = sum(a.elapsed_time(b) for _, a, b in conv_events)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 fprop+dgrad)",
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_timed": len(conv_events),
+            "share_of_step": tc_ms / ms_total if ms_total else None}
 
 
 def run_sampler(args, wl):
@@ -337,9 +443,6 @@ def main():
     ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if wl.get("predict"):
-        run_predict(args, wl)
-        return
     if wl.get("sampler"):
         if args.impl == "reference":
             raise SystemExit("the sampler workload has no separate reference arm: its line carries the host procedure as cpu_baseline")
@@ -347,6 +450,9 @@ def main():
         return
     if args.impl == "reference":
         run_reference_arm(args, wl)
+        return
+    if wl.get("predict"):
+        run_predict(args, wl)
         return
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: >= 3 warm-up steps
@@ -429,28 +535,14 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0 if peaks else 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else \
-        "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
-    tc_flops = sum(f for f, _, _ in conv_events)
-    tc_ms = sum(a.elapsed_time(b) for _, a, b in conv_events)
-    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     traffic, traffic_src = None, None
     if args.workload == "cfg3":
         try:                                  # DRAM bytes per launch of the dominant kernel from the committed ncu capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "static (not measured in this run): " + tj["source"]
         except (OSError, KeyError, ValueError):
             pass
-    roofline = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 fprop+dgrad)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_timed": len(conv_events),
-                "share_of_step": tc_ms / ms if ms else None}
+    roofline = conv_roofline(conv_events, ms, traffic, traffic_src)
     line = {"metric": "UNet3D train voxels/s", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -463,9 +555,9 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
-        # bounded sample of the same workload: ~10-20 s of host work (one 64^3 patch per step, 1 warm-up + 12 timed steps)
-        v, info = cpu_oracle_voxels_per_s(wl, steps=12, warmup=1, edge=min(wl["edge"], 64), batch=1)
-        line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+        # bounded sample of the same workload: ~15-30 s of host work (batch of one on the workload's own patch edge)
+        v, info = cpu_oracle_voxels_per_s(wl, steps=2 if wl["edge"] > 96 else 4, warmup=1, edge=wl["edge"], batch=1)
+        line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": info["kind"],
                                 "sample": info["sample"]}
     else:
         line["cpu_baseline"] = None

@@ -63,24 +63,31 @@ class Storage:
         self.weight = weight if weight is not None else (lambda t: t)
 
     @staticmethod
-    def bf16():
+    def bf16(master_weights=False):
+        """``master_weights``: the convolution weights are rounded to bf16 for the arithmetic but their gradient stays
+        fp32 (fp32 master weights, what the product and mixed-precision training keep); by default the gradient takes the
+        cast's own backward and is rounded to bf16 as well (``model.bfloat16()``)."""
         r = lambda t: t.to(torch.bfloat16).to(torch.float32)
-        return Storage(r, r)
+        rw = (lambda t: t + (r(t) - t).detach()) if master_weights else r
+        return Storage(r, rw)
 
 
 _FP32 = Storage()
 
 
-def single_conv(x, sd, prefix, order, num_groups, st=_FP32, join=None):
+def single_conv(x, sd, prefix, order, num_groups, st=_FP32, join=None, trace=None):
     """One order-string layer (components.py:12-67, :70-90).
 
     Note the reference re-binds ``num_groups`` inside its loop (components.py:53-54, quirk
     Q13); with a single 'g' per order string this has no further effect.
     ``join``: optional (residual, non-linearity letter) applied after the last op of the layer
     (components.py:177-178) before the result is stored.
+    ``trace``: optional list; receives ("layer", prefix, input, output) -- the tensors a layer-wise (teacher-forced)
+    parity test feeds to / expects from the product's layer.
     """
     assert "c" in order and order[0] not in _NONLIN
     n = len(order)
+    x_in = x
     for i, ch in enumerate(order):
         if ch == "c":
             bias = sd.get(prefix + "conv.bias")       # present only without g/b (components.py:43)
@@ -99,13 +106,15 @@ def single_conv(x, sd, prefix, order, num_groups, st=_FP32, join=None):
         # a tensor is materialised after an op unless a non-linearity (fused into that op) follows
         if last or order[i + 1] not in _NONLIN:
             x = st.act(x)
+    if trace is not None:
+        trace.append(("layer", prefix, x_in, x))
     return x
 
 
-def double_conv(x, sd, prefix, order, num_groups, st=_FP32):
+def double_conv(x, sd, prefix, order, num_groups, st=_FP32, trace=None):
     """components.py:114-133 -- channel counts are implied by the weights."""
-    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups, st)
-    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups, st)
+    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups, st, trace=trace)
+    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups, st, trace=trace)
 
 
 def ext_resnet_block(x, sd, prefix, order, num_groups, st=_FP32):
@@ -119,23 +128,33 @@ def ext_resnet_block(x, sd, prefix, order, num_groups, st=_FP32):
 
 
 def unet3d_forward(sd, x, f_maps=64, layer_order="gcr", num_groups=8, testing=False,
-                   final_sigmoid=False, storage=_FP32):
-    """UNet3D.forward, model.py:84-110."""
+                   final_sigmoid=False, storage=_FP32, trace=None):
+    """UNet3D.forward, model.py:84-110.  ``trace``: see single_conv; additionally receives ("pool", i, in, out),
+    ("join", j, skip, low, concat) and ("final", input, logits)."""
     f_maps = feature_ladder(f_maps, 4)
     st = storage
     x = st.act(x)
     skips = []
     for i in range(len(f_maps)):
         if i > 0:
+            x_in = x
             x = F.max_pool3d(x, 2)                               # components.py:210,224
-        x = double_conv(x, sd, f"encoders.{i}.basic_module.", layer_order, num_groups, st)
+            if trace is not None:
+                trace.append(("pool", i, x_in, x))
+        x = double_conv(x, sd, f"encoders.{i}.basic_module.", layer_order, num_groups, st, trace=trace)
         skips.insert(0, x)
     skips = skips[1:]
     for j, skip in enumerate(skips):
+        low = x
         x = F.interpolate(x, size=skip.shape[2:], mode="nearest")   # components.py:277-278
         x = torch.cat((skip, x), dim=1)                              # components.py:280
-        x = double_conv(x, sd, f"decoders.{j}.basic_module.", layer_order, num_groups, st)
+        if trace is not None:
+            trace.append(("join", j, skip, low, x))
+        x = double_conv(x, sd, f"decoders.{j}.basic_module.", layer_order, num_groups, st, trace=trace)
+    x_in = x
     x = F.conv3d(x, sd["final_conv.weight"], sd["final_conv.bias"])   # model.py:102
+    if trace is not None:
+        trace.append(("final", x_in, x))
     if testing:
         x = torch.sigmoid(x) if final_sigmoid else torch.softmax(x, dim=1)
     return x

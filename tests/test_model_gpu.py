@@ -221,3 +221,64 @@ def test_async_weight_gradients_match_the_synchronous_path():
         assert float(opt.flat_grad.abs().sum()) == 0.0
     assert torch.equal(grads[0], grads[1])
     assert float(grads[0].abs().sum()) > 0
+
+
+def test_resume_restores_optimizer_state_and_reproduces_the_uninterrupted_run(tmp_path):
+    """pytorch-lightning's resume_from_checkpoint (examples/train_seg.py:122-131) restores the weights AND the Adam
+    moments / step count: 3 steps + save + load into a fresh module/optimiser + 3 steps == 6 uninterrupted steps,
+    bit for bit (deterministic kernels)."""
+    def make():
+        torch.manual_seed(5)
+        hp = argparse.Namespace(in_channels=1, out_channels=2, fmaps=[16, 32], learning_rate=3e-3, num_workers=0,
+                                batch_size=2, loss="DICE", loss_weight=[0.3, 0.7])
+        net = SegmentationUNet3D(hp).to(DEV)
+        return net, net.configure_optimizers()
+
+    g = torch.Generator().manual_seed(0)
+    batches = [{"data": torch.randn(2, 1, 16, 16, 16, generator=g).to(DEV),
+                "label": torch.randint(0, 2, (2, 1, 16, 16, 16), generator=g, dtype=torch.uint8).to(DEV)} for _ in range(6)]
+
+    def run(net, opt, bs):
+        for i, b in enumerate(bs):
+            net.training_step(b, i)["loss"].backward()
+            opt.step()
+            opt.zero_grad()
+
+    ref_net, ref_opt = make()
+    run(ref_net, ref_opt, batches)
+    net, opt = make()
+    run(net, opt, batches[:3])
+    path = str(tmp_path / "resume.ckpt")
+    net.save_checkpoint(path, opt, 0, 3)
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    st = ckpt["optimizer_states"][0]
+    assert len(st["state"]) == len(list(net.parameters())) and float(st["state"][0]["step"]) == 3.0
+    assert st["state"][0]["exp_avg"].abs().sum() > 0
+    # torch.optim.Adam's own format: a stock Adam over the same parameters accepts it
+    torch.optim.Adam([torch.nn.Parameter(torch.zeros_like(p)) for p in net.parameters()]).load_state_dict(st)
+    net2, opt2 = make()
+    with torch.no_grad():
+        for p in net2.parameters():
+            p.add_(1.0)                                           # must be overwritten by the checkpoint
+    net2.load_state_dict(ckpt["state_dict"])
+    opt2.load_state_dict(st)
+    run(net2, opt2, batches[3:])
+    for (k, a), (_, b) in zip(ref_net.state_dict().items(), net2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # without the optimiser state the continuation differs (the bug the advisor flagged)
+    net3, opt3 = make()
+    net3.load_state_dict(ckpt["state_dict"])
+    run(net3, opt3, batches[3:])
+    assert any(not torch.equal(a, b) for a, b in zip(ref_net.state_dict().values(), net3.state_dict().values()))
+
+
+def test_class_weight_length_and_label_range_are_checked():
+    logits = torch.randn(1, 3, 8, 8, 8, device=DEV)
+    y = torch.randint(0, 3, (1, 8, 8, 8), device=DEV)
+    from mednet_b200.unet.loss import CrossEntropyLoss
+    with pytest.raises(RuntimeError, match="all 3 classes"):
+        DiceLoss(weight=torch.tensor([0.05, 1.0]))(logits, y)
+    with pytest.raises(RuntimeError, match="all 3 classes"):
+        CrossEntropyLoss(weight=torch.tensor([0.05, 1.0]))(logits, y)
+    y[0, 0, 0, 0] = 255                                           # e.g. an ignore label the reference would assert on
+    assert torch.isnan(CrossEntropyLoss(weight=torch.tensor([0.2, 0.3, 0.5]))(logits, y.to(torch.uint8)))

@@ -61,11 +61,25 @@ def main():
                     shown += 1
                 off += n
     ok = rel < 1e-6 and float(b.abs().sum()) > 0
+    # tile-sharded sliding-window inference (dataset.py:349-389, 444-474): every rank ends with the volume a single rank
+    # produces, bit for bit (tiles are independent; only each rank's own centre crops are exchanged)
+    import numpy as np
+    from mednet_b200.predict import SlidingWindowPredictor
+    torch.manual_seed(3)
+    pnet = UNet3D(1, 2 + 3, False, f_maps=[16, 32]).to(dev)
+    with torch.no_grad():
+        pnet.final_conv.weight.mul_(40.0)
+    pnet.eval()
+    vol = np.random.default_rng(0).standard_normal((1, 70, 45, 52)).astype(np.float32)
+    single = SlidingWindowPredictor(pnet, [32] * 3, [4] * 3, 2, batch_size=1)(vol)
+    sharded = SlidingWindowPredictor(pnet, [32] * 3, [4] * 3, 2, batch_size=1, rank=rank, world=world)(vol)
+    predict_ok = bool(torch.equal(single, sharded))
+    ok = ok and predict_ok
     out = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(out, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"dp_check": "ok" if out.item() == 1.0 else "MISMATCH", "world": world, "buckets": nb,
-                          "rel_diff_overlapped_vs_plain": rel}))
+                          "rel_diff_overlapped_vs_plain": rel, "sharded_predict_equals_single_rank": predict_ok}))
     dist.destroy_process_group()
     sys.exit(0 if out.item() == 1.0 else 1)
 

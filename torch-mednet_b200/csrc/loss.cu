@@ -270,7 +270,9 @@ __global__ void ce_partial_kernel(const T* __restrict__ logits, const void* __re
     for (int c = 0; c < CM; ++c)
       if (c < C) sum += expf(z[c] - mx);
     const float nll = logf(sum) + mx - zy;
-    const float w = weight ? weight[y] : 1.f;
+    // a label outside [0, C) is a caller error (nn.CrossEntropyLoss device-asserts): never index weight[] with it, and
+    // poison the loss so that it cannot pass silently
+    const float w = ((unsigned)y < (unsigned)C) ? (weight ? weight[y] : 1.f) : NAN;
     acc[0] += w * nll;
     acc[1] += w;
   }
@@ -303,7 +305,7 @@ __global__ void ce_bwd_kernel(const T* __restrict__ logits, const void* __restri
     float p[CM];
     voxel_probs<T, CM>(logits + n * bstride + s, S, C, 0, p);
     const int y = load_label<TL>(labels, i);
-    const float w = (weight ? weight[y] : 1.f) * scale;
+    const float w = (((unsigned)y < (unsigned)C) ? (weight ? weight[y] : 1.f) : NAN) * scale;
     TO* out = dlogits + n * bstride_out + s;
 #pragma unroll
     for (int c = 0; c < CM; ++c)

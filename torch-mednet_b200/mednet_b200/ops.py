@@ -264,12 +264,14 @@ def k_wgrad(a, b, gather, impl="auto", want_bias=False):
 # on a SIDE stream and accumulated straight into that buffer: the tensor-core wgrad kernels then overlap the memory-bound
 # GroupNorm / pool / join backward kernels of the following layers instead of running between them.
 _side_streams = {}
-_async_pending = False
+_async_pending = set()          # device indices with weight gradients in flight on their side stream
 async_grad_listener = None      # callable(param): told when a parameter's gradient has been ENQUEUED on the side stream
                                 # (the data-parallel reducer counts its bucket down and launches the all-reduce behind it)
 
 
 def side_stream(device=None):
+    if isinstance(device, int):
+        device = torch.device("cuda", device)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _side_streams:
@@ -282,12 +284,13 @@ def mark_async_grad(param, enabled=True):
     param._mednet_async_grad = bool(enabled)
 
 
-def sync_async_wgrad():
-    """Make the current stream wait for every weight gradient enqueued on the side stream."""
-    global _async_pending
-    if _async_pending:
-        torch.cuda.current_stream().wait_stream(side_stream())
-        _async_pending = False
+def sync_async_wgrad(device=None):
+    """Make the current stream of `device` (default: the current device) wait for every weight gradient enqueued on
+    that device's side stream."""
+    key = torch.cuda.current_device() if device is None else torch.device(device).index
+    if key in _async_pending:
+        torch.cuda.current_stream(key).wait_stream(side_stream(key))
+        _async_pending.discard(key)
 
 
 def _async_wgrad_ok(weight):
@@ -316,14 +319,13 @@ def k_wgrad_into(a, b, gather, impl, dw, accumulate=True):
 
 def wgrad_async(a, b, gather, impl, weight):
     """Enqueue dW += wgrad(a, b) into weight.grad on the side stream (see the section comment)."""
-    global _async_pending
-    main, side = torch.cuda.current_stream(), side_stream(a.device)
+    main, side = torch.cuda.current_stream(a.device), side_stream(a.device)
     side.wait_stream(main)                       # a / b (dpre, x) were produced on the main stream
     with torch.cuda.stream(side):
         k_wgrad_into(a, b, gather, impl, weight.grad, accumulate=True)
     a.record_stream(side)                        # the caching allocator must not recycle them before the side stream is done
     b.record_stream(side)
-    _async_pending = True
+    _async_pending.add(a.device.index)
     if async_grad_listener is not None:
         async_grad_listener(weight)
 
@@ -515,8 +517,16 @@ def _logit_view(t):
     return t, n, c, s, (t.stride(0) if n > 1 else c * s)
 
 
+def _check_class_weight(weight, c, what):
+    """The kernels index weight[class]: a weight vector of another length is a caller error (the reference raises a
+    shape mismatch in DiceLoss / a size check in nn.CrossEntropyLoss; e.g. --loss_weight 0.05 1.0 with 3 classes)."""
+    if weight is not None and weight.numel() != c:
+        raise RuntimeError(f"{what}: weight tensor should be defined for all {c} classes, got {weight.numel()} values")
+
+
 def k_dice_fwd(logits, labels, weight, eps, sigmoid):
     _need_cuda(logits, labels)
+    _check_class_weight(weight, logits.shape[1], "DiceLoss")
     logits, n, c, s, bs = _logit_view(logits)
     labels = labels.contiguous()
     dev = logits.device
@@ -548,6 +558,7 @@ def k_dice_bwd(logits, labels, weight, sums, grad_out, eps, sigmoid, out=None, o
 
 def k_ce_fwd(logits, labels, weight):
     _need_cuda(logits, labels)
+    _check_class_weight(weight, logits.shape[1], "CrossEntropyLoss")
     logits, n, c, s, bs = _logit_view(logits)
     labels = labels.contiguous()
     dev = logits.device
@@ -576,6 +587,7 @@ def k_ce_bwd(logits, labels, weight, sums, grad_out, out=None, out_batch_stride=
 
 def k_hm_fwd(pred, target, weight, l1):
     _need_cuda(pred, target, weight)
+    _check_class_weight(weight, pred.shape[1], "heatmap regression loss")
     pred, n, L, s, bs = _logit_view(pred)
     target = target.contiguous()
     dev = pred.device

@@ -2,7 +2,8 @@
 resident on the GPU: gather tile -> network -> uint8 epilogue -> centre-crop scatter.  The reference moves
 fp32 logits and int64 argmax to the host for every batch (predict.py:90-91); here only the final uint8
 volume leaves the device.  Tiles are independent, so ranks take tiles round-robin with no data-path
-collective; the disjoint uint8 sub-volumes are combined once at the end.
+collective; once per volume every rank all-gathers the centre crops of the other ranks' tiles (uint8, only the regions
+each rank produced -- no reduction over the whole volume) and scatters them into its copy of the result.
 """
 from __future__ import annotations
 
@@ -45,6 +46,11 @@ class SlidingWindowPredictor:
         result = torch.zeros((out_channels, X, Y, Z), dtype=torch.uint8, device=dev)
         org_dev = torch.as_tensor(np.ascontiguousarray(mine), dtype=torch.int32, device=dev)
         self.tiles_done = 0
+        share = combine and self.world > 1 and dist.is_initialized()
+        crop = [P[k] - 2 * O[k] for k in range(3)]
+        if share:                                   # centre crops of this rank's tiles, padded to the largest share
+            n_max = -(-len(origins) // self.world)
+            crops = torch.zeros((n_max, out_channels, *crop), dtype=torch.uint8, device=dev)
         for b0 in range(0, len(mine), self.batch_size):
             b = min(self.batch_size, len(mine) - b0)
             org = org_dev[b0:b0 + b].contiguous()
@@ -59,7 +65,20 @@ class SlidingWindowPredictor:
                       B=b, Co=out_channels, X=X, Y=Y, Z=Z, P0=P[0], P1=P[1], P2=P[2], O0=O[0], O1=O[1], O2=O[2])
             check(lib().mednet_tile_scatter(_abi.C.byref(sp), ops._stream()), "tile_scatter")
             ops._count(2)
+            if share:
+                crops[b0:b0 + b] = u8[:, :, O[0]:P[0] - O[0], O[1]:P[1] - O[1], O[2]:P[2] - O[2]]
             self.tiles_done += b
-        if combine and self.world > 1 and dist.is_initialized():
-            dist.all_reduce(result, op=dist.ReduceOp.MAX)     # destination regions are disjoint across ranks
+        if share:
+            gathered = torch.empty((self.world,) + tuple(crops.shape), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered, crops)
+            for r in range(self.world):
+                theirs = origins[r::self.world]
+                if r == self.rank or len(theirs) == 0:
+                    continue
+                org = torch.as_tensor(np.ascontiguousarray(theirs), dtype=torch.int32, device=dev)
+                sp = make("mednet_tile_scatter_params", tiles=gathered[r].data_ptr(), volume=result.data_ptr(),
+                          origins=org.data_ptr(), B=len(theirs), Co=out_channels, X=X, Y=Y, Z=Z, P0=crop[0], P1=crop[1],
+                          P2=crop[2], O0=0, O1=0, O2=0)
+                check(lib().mednet_tile_scatter(_abi.C.byref(sp), ops._stream()), "tile_scatter")
+                ops._count()
         return result

@@ -30,12 +30,22 @@ class Trainer:
         opt = model.configure_optimizers()
         start_epoch, step = 0, 0
         if self.resume:
+            # pytorch-lightning's resume_from_checkpoint (examples/train_seg.py:122-131): weights, epoch / step counters
+            # AND the optimiser state (Adam moments + step count), so the resumed run continues the uninterrupted one
             ckpt = torch.load(self.resume, map_location="cpu", weights_only=False)
             model.load_state_dict(ckpt["state_dict"])
             start_epoch, step = ckpt.get("epoch", 0), ckpt.get("global_step", 0)
+            states = ckpt.get("optimizer_states")
+            if states:
+                opt.load_state_dict(states[0])
         reducer = None
         if world > 1:
-            reducer = BucketedAllReduce(opt.grad_slices(), opt.flat_grad)
+            import torch.distributed as dist
+            flat = opt.flat_grad                               # materialises the flat parameter / gradient buffers
+            dist.broadcast(opt._flat, src=0)                   # replicas start from rank 0's weights (PL's DDP does this)
+            dist.broadcast(opt._m, src=0)
+            dist.broadcast(opt._v, src=0)
+            reducer = BucketedAllReduce(opt.grad_slices(), flat)
         opt.zero_grad()
         for epoch in range(start_epoch, self.max_epochs):
             model.current_epoch = epoch
