@@ -29,7 +29,8 @@ import torch.nn.functional as F
 def cosine(a, b):
     a = torch.as_tensor(a).detach().cpu().double().flatten()
     b = torch.as_tensor(b).detach().cpu().double().flatten()
-    return F.cosine_similarity(a, b, dim=0).item()
+    # not F.cosine_similarity: it clamps the norm product at 1e-8, which small-magnitude gradients fall below
+    return (torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300)).item()
 
 
 def relerr(a, b):

@@ -37,7 +37,9 @@ def relerr(a, b):
 
 
 def cosine(a, b):
-    return F.cosine_similarity(a.detach().double().flatten(), b.detach().double().flatten(), dim=0).item()
+    # not F.cosine_similarity: it clamps the norm product at 1e-8, which deep-layer gradients (norms ~1e-9) fall below
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    return (torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300)).item()
 
 
 def r16(t):

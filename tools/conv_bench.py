@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--wt-fastest", type=int, default=1)
     ap.add_argument("--pair-planes", type=int, default=1)
     ap.add_argument("--d-fastest", type=int, default=1)
+    ap.add_argument("--kd-merge", type=int, default=1)
     ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
@@ -52,6 +53,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"wgrad_wt_fastest", a.wt_fastest), "set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_pair_planes", a.pair_planes), "set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_d_fastest", a.d_fastest), "set_option")
+    check(lib().mednet_tcgen05_set_option(b"kd_merge", a.kd_merge), "set_option")
     layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
     for cin, cout, div in layers:
         s = a.edge // div
@@ -64,13 +66,13 @@ def main():
             wp = ops.k_pack_weights(w, cin, cout, x.dtype, 2 if impl == 2 else 0)
             ms = timed(lambda: ops.k_conv3(x, wp, cout, (s, s, s), 0, impl), a.reps)
             print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="fprop", impl=impl, ms=ms, tflops=flops / ms / 1e9,
-                                  dual_issue=a.dual_issue)))
+                                  dual_issue=a.dual_issue, kd_merge=a.kd_merge)))
         if "dgrad" in a.passes:
             impl = ops.conv_select_impl(dy.shape, (s, s, s), cout, cin, dy.dtype, 0, "auto", dy.data_ptr())
             wp = ops.k_pack_weights(w, cin, cout, dy.dtype, 3 if impl == 2 else 1)
             ms = timed(lambda: ops.k_conv3(dy, wp, cin, (s, s, s), 0, impl), a.reps)
             print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="dgrad", impl=impl, ms=ms, tflops=flops / ms / 1e9,
-                                  dual_issue=a.dual_issue)))
+                                  dual_issue=a.dual_issue, kd_merge=a.kd_merge)))
         if "wgrad" in a.passes:
             ms = timed(lambda: ops.k_wgrad(dy, x, 0, a.wgrad_impl), a.reps)
             print(json.dumps(dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", impl=a.wgrad_impl, ms=ms, tflops=flops / ms / 1e9,

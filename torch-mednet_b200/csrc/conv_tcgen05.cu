@@ -47,6 +47,7 @@ static int g_dense_halo[3] = {0, 0, 0};        // 0: halo rows padded to a 16-vo
                                                // 1: dense 10-voxel pitch, one TMA box per halo plane
 static int g_base_offset_mode[3] = {1, 1, 1};  // 0: base_offset = 0; 1: (addr >> 7) & 7; 2: (addr / row_bytes) & 7
 static int g_dual_issue = 1;                  // mednet_tcgen05_set_option("dual_issue", 0|1)
+static int g_kd_merge = 1;                    // mednet_tcgen05_set_option("kd_merge", 0|1): kd-merged wide-N MMAs (see TcConv::mt)
 static inline int rb_class(int rb) { return rb == 128 ? 0 : rb == 64 ? 1 : 2; }
 
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
@@ -60,6 +61,17 @@ struct TcConv {
   int TD, Ntile, nchunks, RB, pitch, per_row, bo_mode;
   int plane_bytes, b_bytes, BS, acc_stages, tmem_cols;
   int dual;                    // 1: two MMA-issuing threads, each owning half of the brick's d-planes
+  // kd-merged MMAs (plain conv, output tiles <= 128 channels).  The window (kh,kw) of halo plane p is the A operand of
+  // up to three taps -- kd = 0,1,2 feeding the accumulators of d-planes p, p-1, p-2 -- so with the accumulators laid out
+  // in TMEM in DECREASING d order and the three kd weight tiles of one (kh,kw) adjacent in shared memory, ONE MMA with
+  // N = mt*Ntile computes mt taps while reading the 4 KB A window once instead of mt times: the 64-channel-output layers
+  // go from shared-memory bound (A 4 KB + B 2 KB = 48 clk for 32 clk of math per tap) to math bound (10 KB = 80 clk for
+  // 96 clk), and one issuing thread suffices (one instruction per >= 64 clk of math).  mt = taps per MMA (1 = off).
+  int mt;
+  int b_tile;                  // bytes of one [Ntile x chunk] weight tile (a B stage holds 3 of them in kd-merged mode)
+  int a_stages;                // halo sets in shared memory.  The kd-merged order needs every plane until the last (kh,kw)
+                               // window, so it works on 32-channel chunks with TWO halo sets: the next chunk streams in
+                               // under the current chunk's MMAs (with one set the tensor pipe idles for a halo load per chunk)
   // Parity classes of the stride-2 transposed convolution (components.py:259-264).  A plain conv has one class with all
   // 27 taps.  Transposed fprop: 8 OUTPUT classes (output voxel = 2j + parity), each a sub-conv over the input grid with
   // 1/2/4/8 taps; transposed dgrad: 8 INPUT classes (A read at 2j + parity through a stride-2 TMA map) accumulated into
@@ -86,6 +98,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConv& p, int64_t t) {
   c.d0 = (int)(t % p.tiles_d) * p.TD;
   c.n = (int)(t / p.tiles_d);
   return c;
+}
+
+// descriptor-address offset (16-byte units) of window (kh, kw) = g / 3, g % 3 inside a halo plane
+__device__ __forceinline__ uint32_t tapoff9(int g, uint32_t tap_h, uint32_t tap_w) {
+  const uint32_t kh = (uint32_t)g / 3u, kw = (uint32_t)g - kh * 3u;
+  return kh * tap_h + kw * tap_w;
 }
 
 template <int ACT>
@@ -119,11 +137,13 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
       const int64_t vox = (((int64_t)tc_.n * p.OD + od) * p.OH + oh) * p.OW + ow;
       bf16* yrow = p.y + vox * p.Nout + tc_.n0;
       const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + (uint32_t)dz) * (uint32_t)p.Ntile;
+      const uint32_t dcol = p.mt > 1 ? (uint32_t)(p.TD - 1 - dz) : (uint32_t)dz;     // kd-merged mode: decreasing d order
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + dcol) * (uint32_t)p.Ntile;
       for (int j = 0; j < p.Ntile; j += 16) {
         uint32_t r[16];
         tc::tmem_ld_x16(taddr + (uint32_t)j, r);
         tc::tmem_ld_wait();
+        if (p.mt > 1) tc::tmem_st_x16_zero(taddr + (uint32_t)j);     // kd-merged mode: every MMA accumulates
         if (inb) {
           float v[16];
 #pragma unroll
@@ -154,6 +174,7 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
         }
       }
     }
+    if (p.mt > 1) tc::tmem_st_wait();
     tc::tc_fence_before();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
@@ -165,11 +186,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
-  uint8_t* b_base = a_base + (size_t)(p.TD + 2) * p.plane_bytes;
+  uint8_t* b_base = a_base + (size_t)p.a_stages * (p.TD + 2) * p.plane_bytes;
   uint64_t* bars = (uint64_t*)(b_base + (size_t)p.BS * p.b_bytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + MAX_PLANES;
-  uint64_t* b_full = bars + 2 * MAX_PLANES;
+  uint64_t* a_full = bars;                       // [a_stages][MAX_PLANES]
+  uint64_t* a_empty = bars + 2 * MAX_PLANES;
+  uint64_t* b_full = bars + 4 * MAX_PLANES;
   uint64_t* b_empty = b_full + MAX_BSTAGES;
   uint64_t* acc_full = b_empty + MAX_BSTAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -180,7 +201,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   if (threadIdx.x == 0) {
     const uint32_t nissue = p.dual ? 2u : 1u;         // every issuer commits to the barriers the MMAs release
-    for (int i = 0; i < nplanes; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], nissue); }
+    for (int st = 0; st < p.a_stages; ++st)
+      for (int i = 0; i < nplanes; ++i) {
+        tc::mbar_init(&a_full[st * MAX_PLANES + i], 1);
+        tc::mbar_init(&a_empty[st * MAX_PLANES + i], nissue);
+      }
     for (int i = 0; i < p.BS; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], nissue); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], nissue); tc::mbar_init(&acc_empty[i], 4); }
     tc::fence_barrier_init();
@@ -196,6 +221,16 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int KC = p.RB / 2;
+  if (p.mt > 1) {
+    // kd-merged mode: accumulators start at zero (the epilogue re-zeroes what it reads)
+    if (warp >= 3 && warp <= 6) {
+      for (int col = 0; col < p.tmem_cols; col += 16) tc::tmem_st_x16_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col);
+      tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
 
   if (warp == 0) {
     // ===================== halo (A) producer =====================
@@ -207,16 +242,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int s = p.in_scale;
           const int cw = s * (tc_.w0 - 1) + (ci & 1), ch = s * (tc_.h0 - 1) + ((ci >> 1) & 1), cd0 = s * (tc_.d0 - 1) + (ci >> 2);
           for (int c = 0; c < p.nchunks; ++c, ++ait) {
+            const uint32_t ast = ait % (uint32_t)p.a_stages, aph = (ait / (uint32_t)p.a_stages) & 1u;
+            uint64_t* full = a_full + ast * MAX_PLANES;
+            uint64_t* empty = a_empty + ast * MAX_PLANES;
             for (int pl = 0; pl < nplanes; ++pl) {
-              tc::mbar_wait(&a_empty[pl], (ait & 1u) ^ 1u);
-              tc::mbar_arrive_expect_tx(&a_full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
-              uint8_t* dst = a_base + (size_t)pl * p.plane_bytes;
+              tc::mbar_wait(&empty[pl], aph ^ 1u);
+              tc::mbar_arrive_expect_tx(&full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
+              uint8_t* dst = a_base + (size_t)(ast * nplanes + pl) * p.plane_bytes;
               if (p.per_row) {
                 for (int ph = 0; ph < HALO_H; ++ph)
-                  tc::tma_load_5d(dst + (size_t)ph * p.pitch * p.RB, &map_x, &a_full[pl], c * KC, cw, ch + s * ph,
+                  tc::tma_load_5d(dst + (size_t)ph * p.pitch * p.RB, &map_x, &full[pl], c * KC, cw, ch + s * ph,
                                   cd0 + s * pl, tc_.n);
               } else {
-                tc::tma_load_5d(dst, &map_x, &a_full[pl], c * KC, cw, ch, cd0 + s * pl, tc_.n);
+                tc::tma_load_5d(dst, &map_x, &full[pl], c * KC, cw, ch, cd0 + s * pl, tc_.n);
               }
             }
           }
@@ -233,6 +271,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int wcls = p.ncls_out > 1 ? tc_.cls : ci;          // weight set / tap mask of this (tile, input class)
           const uint32_t mask = p.tapmask[wcls];
           for (int c = 0; c < p.nchunks; ++c) {
+            if (p.mt > 1) {
+              // kd-merged mode: one stage = the three kd tiles of one (kh,kw), adjacent in shared memory
+              for (int g = 0; g < 9; ++g) {
+                const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
+                ++bit;
+                tc::mbar_wait(&b_empty[st], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(3 * p.b_tile));
+                for (int kd = 0; kd < 3; ++kd)
+                  tc::tma_load_2d(b_base + (size_t)st * p.b_bytes + (size_t)kd * p.b_tile, &map_w, &b_full[st], c * KC,
+                                  (kd * 9 + g) * p.Nout + tc_.n0);
+              }
+              continue;
+            }
             for (int tap = 0; tap < 27; ++tap) {
               if (!((mask >> tap) & 1u)) continue;
               const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
@@ -271,6 +322,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 9; ++i) tapoff[i] = (uint32_t)(((i / 3) * p.pitch + (i % 3)) * p.RB) >> 4;
       const int ksteps = p.RB / 32;
+      // kd-merged mode constants
+      const uint32_t ntile = (uint32_t)p.Ntile, tile16 = (uint32_t)p.b_tile >> 4, dcol_top = (uint32_t)((p.TD - 1) * p.Ntile);
+      const uint32_t id1 = idesc, id2 = tc::make_idesc_bf16(128, 2 * p.Ntile <= 256 ? 2 * p.Ntile : 8, 0, 0),
+                     id3 = tc::make_idesc_bf16(128, 3 * p.Ntile <= 256 ? 3 * p.Ntile : 8, 0, 0);
+      const uint32_t tap_h = (uint32_t)(p.pitch * p.RB) >> 4, tap_w = (uint32_t)p.RB >> 4;
       uint32_t ait = 0, bit = 0, tcount = 0;
       uint32_t bst = 0, bph = 0;                       // B ring position (stage, parity) without div/mod
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
@@ -283,14 +339,58 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int ci = 0; ci < p.ncls_in; ++ci) {
           const uint32_t mask = p.tapmask[out_cls >= 0 ? out_cls : ci];
           for (int c = 0; c < p.nchunks; ++c, ++ait) {
+            const uint32_t ast = ait % (uint32_t)p.a_stages, aph = (ait / (uint32_t)p.a_stages) & 1u;
+            uint64_t* a_full_s = a_full + ast * MAX_PLANES;
+            uint64_t* a_empty_s = a_empty + ast * MAX_PLANES;
+            const uint32_t a_lo_s = a_lo0 + ast * (uint32_t)nplanes * plane16;
+            if (p.mt > 1) {
+              // ---- kd-merged issue order: (kh,kw) outer, halo plane inner; see TcConv::mt.  Every accumulator column is
+              // zero when its tile starts (the epilogue clears what it has read), so all MMAs accumulate.  Planes 0 / 1
+              // reach 1 / 2 d-planes, the interior planes 3, planes TD / TD+1 again 2 / 1:
+              //   plane pl, taps kd_lo..kd_hi -> accumulators dz = pl-kd_lo .. pl-kd_hi = columns (TD-1-dz)*Ntile ascending
+              for (int g = 0; g < 9; ++g) {
+                tc::mbar_wait(&b_full[bst], bph);
+                tc::tc_fence_after();
+                const uint32_t b0 = b_lo0 + bst * b16, b1 = b0 + tile16, b2 = b1 + tile16;
+                uint32_t a = a_lo_s + tapoff9(g, tap_h, tap_w);
+                const bool first_g = g == 0, last_g = g == 8;
+#define KDM_PLANE(PL, DCOL, BLO, IDESC)                                                          \
+                {                                                                                \
+                  if (first_g) { tc::mbar_wait(&a_full_s[PL], aph); tc::tc_fence_after(); }      \
+                  const uint32_t d_ = d_tile + (DCOL);                                           \
+                  if (ksteps == 4) {                                                             \
+                    tc::umma_bf16_lohi(d_, a, a_hi, (BLO), b_hi, (IDESC), 1u);                   \
+                    tc::umma_bf16_lohi(d_, a + 2, a_hi, (BLO) + 2, b_hi, (IDESC), 1u);           \
+                    tc::umma_bf16_lohi(d_, a + 4, a_hi, (BLO) + 4, b_hi, (IDESC), 1u);           \
+                    tc::umma_bf16_lohi(d_, a + 6, a_hi, (BLO) + 6, b_hi, (IDESC), 1u);           \
+                  } else if (ksteps == 2) {                                                      \
+                    tc::umma_bf16_lohi(d_, a, a_hi, (BLO), b_hi, (IDESC), 1u);                   \
+                    tc::umma_bf16_lohi(d_, a + 2, a_hi, (BLO) + 2, b_hi, (IDESC), 1u);           \
+                  } else {                                                                       \
+                    tc::umma_bf16_lohi(d_, a, a_hi, (BLO), b_hi, (IDESC), 1u);                   \
+                  }                                                                              \
+                  if (last_g) tc::umma_commit(&a_empty_s[PL]);                                   \
+                  a += plane16;                                                                  \
+                }
+                KDM_PLANE(0, dcol_top, b0, id1)
+                KDM_PLANE(1, dcol_top - ntile, b0, id2)
+                for (int pl = 2; pl < p.TD; ++pl) KDM_PLANE(pl, dcol_top - (uint32_t)pl * ntile, b0, id3)
+                KDM_PLANE(p.TD, 0u, b1, id2)
+                KDM_PLANE(p.TD + 1, 0u, b2, id1)
+#undef KDM_PLANE
+                tc::umma_commit(&b_empty[bst]);
+                if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
+              }
+              continue;
+            }
             for (int kd = 0; kd < 3; ++kd) {
               if (kd == 0) {
-                for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full[pl], ait & 1u);
+                for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full_s[pl], aph);
               } else {
-                tc::mbar_wait(&a_full[p.TD - 1 + kd], ait & 1u);
+                tc::mbar_wait(&a_full_s[p.TD - 1 + kd], aph);
               }
               tc::tc_fence_after();
-              const uint32_t a_kd = a_lo0 + (uint32_t)kd * plane16;
+              const uint32_t a_kd = a_lo_s + (uint32_t)kd * plane16;
               const uint32_t mask_kd = (mask >> (kd * 9)) & 0x1ffu;
 #pragma unroll
               for (int khw = 0; khw < 9; ++khw) {
@@ -322,9 +422,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               }
               // planes whose last tap phase is this kd can be refilled for the next chunk
               if (kd < 2) {
-                tc::umma_commit(&a_empty[kd]);
+                tc::umma_commit(&a_empty_s[kd]);
               } else {
-                for (int pl = 2; pl < nplanes; ++pl) tc::umma_commit(&a_empty[pl]);
+                for (int pl = 2; pl < nplanes; ++pl) tc::umma_commit(&a_empty_s[pl]);
               }
             }
           }
@@ -389,23 +489,31 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   p.RB = pick_row_bytes(q->K);
   p.Ntile = pick_ntile(q->Nout);
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
-  p.nchunks = q->K / (p.RB / 2);
   // more planes per brick = fewer halo re-reads and weight-tile loads per voxel; TMEM holds TD * Ntile columns per stage
   p.TD = (p.Ntile <= 64 && p.D >= 4) ? 4 : (p.D >= 2 ? 2 : 1);
+  // kd-merged MMAs: plain conv, up to 128-channel output tiles, 32-channel chunks (64-byte rows) so that two halo sets fit
+  p.mt = 1;
+  p.a_stages = 1;
+  if (g_kd_merge && !tf && !tb && p.TD >= 2 && ((p.Ntile * p.RB) % 1024) == 0)
+    p.mt = 3 * p.Ntile <= 256 ? 3 : ((2 * p.Ntile <= 256 && p.TD == 2) ? 2 : 1);
+  p.nchunks = q->K / (p.RB / 2);
   const int rc = rb_class(p.RB);
   if (!g_enabled[rc] || g_base_offset_mode[rc] != 0) return false;   // the kernel issues base_offset = 0 descriptors
   p.per_row = g_dense_halo[rc] ? 0 : 1;
   p.pitch = g_dense_halo[rc] ? HALO_W : 16;
   p.bo_mode = g_base_offset_mode[rc];
   p.plane_bytes = (int)align_up((size_t)HALO_H * p.pitch * p.RB, 1024);
-  p.b_bytes = (int)align_up((size_t)p.Ntile * p.RB, 1024);
+  p.b_tile = p.Ntile * p.RB;                     // a multiple of 1024 in kd-merged mode (Ntile % 16 == 0, 64-byte rows)
+  p.b_bytes = p.mt > 1 ? 3 * p.b_tile : (int)align_up((size_t)p.b_tile, 1024);
   const int budget = 227 * 1024 - 1024 - 1024;   // alignment slack + barrier block
-  int bs = (budget - (p.TD + 2) * p.plane_bytes) / p.b_bytes;
+  if (p.mt > 1 && 2 * (p.TD + 2) * p.plane_bytes + 3 * p.b_bytes <= budget) p.a_stages = 2;
+  int bs = (budget - p.a_stages * (p.TD + 2) * p.plane_bytes) / p.b_bytes;
   if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
+  if (p.mt > 1 && bs > 4) bs = 4;
   if (bs < 2) return false;
   p.BS = bs;
   p.acc_stages = (2 * p.TD * p.Ntile <= 512) ? 2 : 1;
-  p.dual = (g_dual_issue && p.Ntile <= 96 && p.TD >= 2 && (p.TD % 2) == 0) ? 1 : 0;
+  p.dual = (p.mt == 1 && g_dual_issue && p.Ntile <= 96 && p.TD >= 2 && (p.TD % 2) == 0) ? 1 : 0;
   int cols = p.acc_stages * p.TD * p.Ntile, pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
@@ -463,7 +571,7 @@ int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MEDNET_EUNSUPPORTED;
   }
-  const size_t smem = 1024 + (size_t)(p.TD + 2) * p.plane_bytes + (size_t)p.BS * p.b_bytes + 1024;
+  const size_t smem = 1024 + (size_t)p.a_stages * (p.TD + 2) * p.plane_bytes + (size_t)p.BS * p.b_bytes + 1024;
   static std::mutex mu;
   static size_t configured = 0;
   {
@@ -567,6 +675,7 @@ extern "C" int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_ha
 extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
   MEDNET_REQUIRE(name != nullptr, MEDNET_EINVAL);
   if (strcmp(name, "dual_issue") == 0) { g_dual_issue = value ? 1 : 0; return MEDNET_OK; }
+  if (strcmp(name, "kd_merge") == 0) { g_kd_merge = value ? 1 : 0; return MEDNET_OK; }
   if (strcmp(name, "wgrad_wt_fastest") == 0) { tc_wgrad_set_wt_fastest(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_pair_planes") == 0) { tc_wgrad_set_pair_planes(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_d_fastest") == 0) { tc_wgrad_set_d_fastest(value); return MEDNET_OK; }
