@@ -27,8 +27,6 @@ extern "C" size_t mednet_conv3d_workspace_bytes(const mednet_conv3d_params* p) {
 
 extern "C" int mednet_conv3d_fprop(const mednet_conv3d_params* p, void* workspace, size_t workspace_bytes,
                                    mednet_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   MEDNET_REQUIRE(conv_args_ok(p), MEDNET_EINVAL);
   if (p->gather == MEDNET_GATHER_CONV3)
     MEDNET_REQUIRE(p->Di == p->Do && p->Hi == p->Ho && p->Wi == p->Wo, MEDNET_EINVAL);
@@ -38,7 +36,7 @@ extern "C" int mednet_conv3d_fprop(const mednet_conv3d_params* p, void* workspac
     MEDNET_REQUIRE(p->Di == 2 * p->Do && p->Hi == 2 * p->Ho && p->Wi == 2 * p->Wo, MEDNET_EINVAL);
   const int impl = mednet_conv3d_select_impl(p);
   if (impl < 0) return impl;
-  if (impl == MEDNET_IMPL_TCGEN05) return tc_fprop(p, stream);
+  if (impl == MEDNET_IMPL_TCGEN05) return tc_fprop(p, workspace, workspace_bytes, stream);   // workspace: profiling counters only
   return simt_fprop(p, stream);
 }
 

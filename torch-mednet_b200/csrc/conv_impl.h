@@ -14,7 +14,7 @@ int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int ac
                 cudaStream_t st);
 
 bool tc_fprop_supported(const mednet_conv3d_params* p);
-int tc_fprop(const mednet_conv3d_params* p, cudaStream_t st);
+int tc_fprop(const mednet_conv3d_params* p, void* workspace, size_t workspace_bytes, cudaStream_t st);
 bool tc_wgrad_supported(const mednet_wgrad_params* p);
 void tc_wgrad_set_wt_fastest(int v);
 void tc_wgrad_set_pair_planes(int v);

@@ -100,6 +100,18 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConv& p, int64_t t) {
   return c;
 }
 
+// mbarrier wait that, in the profiling instantiation of the kernel, adds the cycles spent waiting to `acc`
+template <bool PROF>
+__device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity, long long& acc) {
+  if (PROF) {
+    const long long t0 = clock64();
+    tc::mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    tc::mbar_wait(bar, parity);
+  }
+}
+
 // descriptor-address offset (16-byte units) of window (kh, kw) = g / 3, g % 3 inside a halo plane
 __device__ __forceinline__ uint32_t tapoff9(int g, uint32_t tap_h, uint32_t tap_w) {
   const uint32_t kh = (uint32_t)g / 3u, kw = (uint32_t)g - kh * 3u;
@@ -116,9 +128,11 @@ __device__ __forceinline__ float act_apply_t(float x, float a) {
 
 // Epilogue of one CTA (warps 3..6, one TMEM lane quadrant each): TMEM -> registers -> (+bias, +addend, activation) -> bf16
 // NDHWC rows.  Accumulator row m = voxel (h, w) of the brick plane.
-template <int ACT>
+template <int ACT, bool PROF>
 __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
-                                              int warp, int lane) {
+                                              int warp, int lane, long long* prof) {
+  long long w_full = 0;
+  const long long t_begin = PROF ? clock64() : 0;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
   const int m = q * 32 + lane;
   const int hh = m >> 3, ww = m & 7;
@@ -126,7 +140,7 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
   for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
     const TileCoord tc_ = decode_tile(p, t);
     const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-    tc::mbar_wait(&acc_full[as], aph);
+    pwait<PROF>(&acc_full[as], aph, w_full);
     tc::tc_fence_after();
     const int h = tc_.h0 + hh, w = tc_.w0 + ww;
     const int oh = p.out_scale * h + ((tc_.cls >> 1) & 1), ow = p.out_scale * w + (tc_.cls & 1);
@@ -179,10 +193,18 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
   }
+  if (PROF && warp == 3 && lane == 0) { prof[4] = clock64() - t_begin; prof[5] = w_full; }
 }
 
+// PROF: per-CTA cycle counters written to prof_out[blockIdx.x * 8 + i] (mednet_tcgen05_set_option("conv_profile", 1)):
+//   0 MMA issuer total, 1 its wait for halo planes, 2 for weight stages, 3 for a free accumulator stage,
+//   4 epilogue warp total, 5 its wait for a finished accumulator, 6 halo producer wait for free planes, 7 weight producer
+//   wait for free stages
+template <bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcConv p) {
+conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcConv p,
+                long long* __restrict__ prof_out) {
+  long long* prof = PROF ? prof_out + (size_t)blockIdx.x * 8 : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
@@ -236,6 +258,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ===================== halo (A) producer =====================
     if (tc::elect_one()) {
       uint32_t ait = 0;
+      long long w_empty = 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, t);
         for (int ci = 0; ci < p.ncls_in; ++ci) {
@@ -246,7 +269,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint64_t* full = a_full + ast * MAX_PLANES;
             uint64_t* empty = a_empty + ast * MAX_PLANES;
             for (int pl = 0; pl < nplanes; ++pl) {
-              tc::mbar_wait(&empty[pl], aph ^ 1u);
+              pwait<PROF>(&empty[pl], aph ^ 1u, w_empty);
               tc::mbar_arrive_expect_tx(&full[pl], (uint32_t)(HALO_H * HALO_W * p.RB));
               uint8_t* dst = a_base + (size_t)(ast * nplanes + pl) * p.plane_bytes;
               if (p.per_row) {
@@ -260,11 +283,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       }
+      if (PROF) prof[6] = w_empty;
     }
   } else if (warp == 1) {
     // ===================== weight (B) producer =====================
     if (tc::elect_one()) {
       uint32_t bit = 0;
+      long long w_empty = 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, t);
         for (int ci = 0; ci < p.ncls_in; ++ci) {
@@ -276,7 +301,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               for (int g = 0; g < 9; ++g) {
                 const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
                 ++bit;
-                tc::mbar_wait(&b_empty[st], ph ^ 1u);
+                pwait<PROF>(&b_empty[st], ph ^ 1u, w_empty);
                 tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(3 * p.b_tile));
                 for (int kd = 0; kd < 3; ++kd)
                   tc::tma_load_2d(b_base + (size_t)st * p.b_bytes + (size_t)kd * p.b_tile, &map_w, &b_full[st], c * KC,
@@ -288,7 +313,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               if (!((mask >> tap) & 1u)) continue;
               const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
               ++bit;
-              tc::mbar_wait(&b_empty[st], ph ^ 1u);
+              pwait<PROF>(&b_empty[st], ph ^ 1u, w_empty);
               tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(p.Ntile * p.RB));
               tc::tma_load_2d(b_base + (size_t)st * p.b_bytes, &map_w, &b_full[st], c * KC,
                               (wcls * 27 + tap) * p.Nout + tc_.n0);
@@ -296,6 +321,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       }
+      if (PROF && warp == 1) prof[7] = w_empty;
     }
   } else if (warp == 2 || warp == 7) {
     // ===================== MMA issuer(s) =====================
@@ -329,9 +355,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const uint32_t tap_h = (uint32_t)(p.pitch * p.RB) >> 4, tap_w = (uint32_t)p.RB >> 4;
       uint32_t ait = 0, bit = 0, tcount = 0;
       uint32_t bst = 0, bph = 0;                       // B ring position (stage, parity) without div/mod
+      long long w_a = 0, w_b = 0, w_acc = 0;
+      const long long t_begin = PROF ? clock64() : 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-        tc::mbar_wait(&acc_empty[as], aph ^ 1u);
+        pwait<PROF>(&acc_empty[as], aph ^ 1u, w_acc);
         tc::tc_fence_after();
         const uint32_t d_tile = tmem_base + as * (uint32_t)(p.TD * p.Ntile) + d_issuer;
         const int out_cls = p.ncls_out > 1 ? decode_tile(p, t).cls : -1;
@@ -349,14 +377,14 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               // reach 1 / 2 d-planes, the interior planes 3, planes TD / TD+1 again 2 / 1:
               //   plane pl, taps kd_lo..kd_hi -> accumulators dz = pl-kd_lo .. pl-kd_hi = columns (TD-1-dz)*Ntile ascending
               for (int g = 0; g < 9; ++g) {
-                tc::mbar_wait(&b_full[bst], bph);
+                pwait<PROF>(&b_full[bst], bph, w_b);
                 tc::tc_fence_after();
                 const uint32_t b0 = b_lo0 + bst * b16, b1 = b0 + tile16, b2 = b1 + tile16;
                 uint32_t a = a_lo_s + tapoff9(g, tap_h, tap_w);
                 const bool first_g = g == 0, last_g = g == 8;
 #define KDM_PLANE(PL, DCOL, BLO, IDESC)                                                          \
                 {                                                                                \
-                  if (first_g) { tc::mbar_wait(&a_full_s[PL], aph); tc::tc_fence_after(); }      \
+                  if (first_g) { pwait<PROF>(&a_full_s[PL], aph, w_a); tc::tc_fence_after(); }   \
                   const uint32_t d_ = d_tile + (DCOL);                                           \
                   if (ksteps == 4) {                                                             \
                     tc::umma_bf16_lohi(d_, a, a_hi, (BLO), b_hi, (IDESC), 1u);                   \
@@ -385,9 +413,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
             for (int kd = 0; kd < 3; ++kd) {
               if (kd == 0) {
-                for (int pl = 0; pl < p.TD; ++pl) tc::mbar_wait(&a_full_s[pl], aph);
+                for (int pl = 0; pl < p.TD; ++pl) pwait<PROF>(&a_full_s[pl], aph, w_a);
               } else {
-                tc::mbar_wait(&a_full_s[p.TD - 1 + kd], aph);
+                pwait<PROF>(&a_full_s[p.TD - 1 + kd], aph, w_a);
               }
               tc::tc_fence_after();
               const uint32_t a_kd = a_lo_s + (uint32_t)kd * plane16;
@@ -395,7 +423,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
               for (int khw = 0; khw < 9; ++khw) {
                 if (!((mask_kd >> khw) & 1u)) continue;
-                tc::mbar_wait(&b_full[bst], bph);
+                pwait<PROF>(&b_full[bst], bph, w_b);
                 tc::tc_fence_after();
                 const uint32_t b_lo = b_lo0 + bst * b16;
                 uint32_t a_lo = a_kd + tapoff[khw];
@@ -432,6 +460,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc::umma_commit(&acc_full[as]);
       }
       (void)bit;
+      if (PROF && issuer == 0) { prof[0] = clock64() - t_begin; prof[1] = w_a; prof[2] = w_b; prof[3] = w_acc; }
     }
   } else {
     // ===================== epilogue =====================
@@ -439,10 +468,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // selects or an indirect branch per element depending on unrelated details of the kernel (measured: 2x slower
     // epilogue-bound layers), so it is dispatched once per CTA here
     switch (p.act) {
-      case MEDNET_ACT_RELU: epilogue_loop<MEDNET_ACT_RELU>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
-      case MEDNET_ACT_LEAKY: epilogue_loop<MEDNET_ACT_LEAKY>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
-      case MEDNET_ACT_ELU: epilogue_loop<MEDNET_ACT_ELU>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
-      default: epilogue_loop<MEDNET_ACT_NONE>(p, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case MEDNET_ACT_RELU: epilogue_loop<MEDNET_ACT_RELU, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
+      case MEDNET_ACT_LEAKY: epilogue_loop<MEDNET_ACT_LEAKY, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
+      case MEDNET_ACT_ELU: epilogue_loop<MEDNET_ACT_ELU, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
+      default: epilogue_loop<MEDNET_ACT_NONE, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
     }
   }
   tc::tc_fence_before();
@@ -451,9 +480,14 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int pick_ntile(int Nout) {
-  if (Nout <= 256) return Nout;
-  for (int t = 256; t >= 16; t -= 16)
+static int g_ntile_max = 128;                 // mednet_tcgen05_set_option("ntile_max", 128|256)
+// Output-channel tile.  Tiles of <= 128 channels keep TWO accumulator stages in TMEM (2 x TD x Ntile <= 512 columns), so
+// the epilogue of one tile overlaps the MMAs of the next (with 192 / 256-channel tiles the MMA issuer waited for the
+// epilogue for up to 29 % of the kernel, tools/conv_profile.py), and they take the kd-merged path (N = 2 * Ntile).
+static int pick_ntile(int Nout, int K) {
+  if (Nout == 256 && K >= 512) return 256;     // long K loops hide the epilogue; the wider MMA wins (768 -> 256: +5 %)
+  if (Nout <= g_ntile_max) return Nout;
+  for (int t = g_ntile_max; t >= 16; t -= 16)
     if (Nout % t == 0) return t;
   return 0;
 }
@@ -487,7 +521,7 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
     p.tapmask[cls] = m;
   }
   p.RB = pick_row_bytes(q->K);
-  p.Ntile = pick_ntile(q->Nout);
+  p.Ntile = pick_ntile(q->Nout, q->K);
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
   // more planes per brick = fewer halo re-reads and weight-tile loads per voxel; TMEM holds TD * Ntile columns per stage
   p.TD = (p.Ntile <= 64 && p.D >= 4) ? 4 : (p.D >= 2 ? 2 : 1);
@@ -539,7 +573,9 @@ bool tc_fprop_supported(const mednet_conv3d_params* q) {
   return plan_tc(q, &p);
 }
 
-int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
+static int g_conv_profile = 0;                // mednet_tcgen05_set_option("conv_profile", 0|1): see conv3_tc_kernel<PROF>
+
+int tc_fprop(const mednet_conv3d_params* q, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   TcConv p;
   if (!plan_tc(q, &p)) return MEDNET_EUNSUPPORTED;
   PFN_encodeTiled enc = get_encode_tiled();
@@ -577,13 +613,18 @@ int tc_fprop(const mednet_conv3d_params* q, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> lock(mu);
     if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(conv3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       configured = smem;
     }
   }
   int64_t grid = p.num_tiles < sm_count_cached() ? p.num_tiles : sm_count_cached();
-  conv3_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, st>>>(map_x, map_w, p);
+  if (g_conv_profile && workspace != nullptr && workspace_bytes >= (size_t)grid * 8 * sizeof(long long))
+    conv3_tc_kernel<true><<<(unsigned)grid, NUM_THREADS, smem, st>>>(map_x, map_w, p, (long long*)workspace);
+  else
+    conv3_tc_kernel<false><<<(unsigned)grid, NUM_THREADS, smem, st>>>(map_x, map_w, p, nullptr);
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }
@@ -676,6 +717,8 @@ extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
   MEDNET_REQUIRE(name != nullptr, MEDNET_EINVAL);
   if (strcmp(name, "dual_issue") == 0) { g_dual_issue = value ? 1 : 0; return MEDNET_OK; }
   if (strcmp(name, "kd_merge") == 0) { g_kd_merge = value ? 1 : 0; return MEDNET_OK; }
+  if (strcmp(name, "conv_profile") == 0) { g_conv_profile = value ? 1 : 0; return MEDNET_OK; }
+  if (strcmp(name, "ntile_max") == 0) { g_ntile_max = value >= 256 ? 256 : 128; return MEDNET_OK; }
   if (strcmp(name, "wgrad_wt_fastest") == 0) { tc_wgrad_set_wt_fastest(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_pair_planes") == 0) { tc_wgrad_set_pair_planes(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_d_fastest") == 0) { tc_wgrad_set_d_fastest(value); return MEDNET_OK; }

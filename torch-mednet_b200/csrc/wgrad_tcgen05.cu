@@ -350,7 +350,9 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
     sg.ut_base = ut_base; sg.u_tiles = u_tiles;
     const int worktypes = u_tiles * a.s_chunks * 2;
     const int64_t bricks = (int64_t)a.N * (a.tiles_d + (paired ? 1 : 0)) * a.tiles_h * a.tiles_w;
-    int64_t ksplit = (2 * sms + worktypes - 1) / worktypes;     // ~2 CTAs per SM per launch: bounded tail
+    // one CTA is resident per SM (224 KB of shared memory): AT MOST two full waves, never a third, nearly empty one
+    // (rounding the split factor up gave e.g. 312 CTAs = 148 + 148 + 16 for 384x128 channels: 30 % of the launch idle)
+    int64_t ksplit = (2 * sms) / worktypes;
     if (ksplit > bricks) ksplit = bricks;
     if (ksplit < 1) ksplit = 1;
     sg.ksplit = (int)ceil_div64(bricks, ceil_div64(bricks, ksplit));
