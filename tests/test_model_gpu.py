@@ -186,8 +186,7 @@ def test_sliding_window_predictor_matches_reference_loop():
 
     want = otiling.sliding_window_predict(vol, forward_fn, [16] * 3, [3] * 3, L, L + 1, batch_size=3)
     got = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=5)(vol).cpu().numpy()
-    mism = (got != want).mean()
-    assert mism < 1e-4, mism                                     # identical kernels; only batch-shape independent
+    assert np.array_equal(got, want)                             # batch-invariant kernels: bit-exact for any tile batching
     # tile sharding: two "ranks" cover disjoint regions whose union is the full result
     a = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=0, world=2)(vol, combine=False)
     b = SlidingWindowPredictor(net, [16] * 3, [3] * 3, L, batch_size=4, rank=1, world=2)(vol, combine=False)

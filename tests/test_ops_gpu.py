@@ -444,3 +444,26 @@ def test_maxpool_with_fused_skip_gradient(c, shape, act):
     y2, _ = ops.MaxPoolSkipFn.apply(xg2, act)
     (y2 * ndhwc(g1)).sum().backward()                       # skip branch unused -> plain pool backward
     assert relerr(ncdhw(xg2.grad), gp) < 1e-6
+
+
+@pytest.mark.parametrize("c,groups", [(1, 1), (16, 8)])
+def test_groupnorm_large_offset_input_matches_welford(c, groups):
+    """Un-normalised intensities (|mean| >> std, e.g. CT values) reach the first GroupNorm of the 'gcr' order
+    (components.py:45-57).  torch's GroupNorm is Welford-based; raw fp32 sums of x and x^2 would cancel catastrophically
+    here (variance 1 out of second moments ~1e6).  The kernels accumulate pivot-shifted sums: same 1e-4 as elsewhere."""
+    torch.manual_seed(0)
+    x = (1000.0 + torch.randn(2, c, 12, 20, 24)).requires_grad_()
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
+    ref = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    xg = ndhwc(x.detach())
+    y = ops.GroupNormActFn.apply(xg, gamma.to(DEV), beta.to(DEV), groups, 0, None)
+    assert relerr(ncdhw(y), ref.detach()) < 1e-4
+    # virtual-concat variant: skip and (upsampled) low with different large offsets
+    if c >= 16:
+        skip = 500.0 + torch.randn(1, c, 8, 8, 8)
+        low = -300.0 + torch.randn(1, c, 4, 4, 4)
+        cat = torch.cat((skip, F.interpolate(low, size=(8, 8, 8), mode="nearest")), dim=1)
+        g2, b2 = torch.rand(2 * c) + 0.5, torch.randn(2 * c)
+        ref2 = F.group_norm(cat, groups, g2, b2, eps=1e-5)
+        y2 = ops.UpcatGroupNormFn.apply(ndhwc(skip), ndhwc(low), g2.to(DEV), b2.to(DEV), groups, 0, 0)
+        assert relerr(ncdhw(y2), ref2) < 1e-4

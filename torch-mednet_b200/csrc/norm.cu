@@ -34,8 +34,13 @@ static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force
     p.coltiles = ceil_div(p.ncol, 256);
     p.R = 1;
   }
+  // The slab count -- and with it the order in which a sample's statistics are summed -- depends on (S, C) only, NOT on
+  // the batch size: a sample gives bit-identical results whatever batch it is evaluated in (the sliding-window predictor
+  // batches tiles freely, examples/predict.py).  Sized for a batch of two filling the GPU; larger batches just launch
+  // more (still >= 4 row steps long) slabs.
+  (void)N;
   int64_t target = (int64_t)sm_count_cached() * slabs_per_sm;
-  int64_t nslab = target / (N * p.coltiles);
+  int64_t nslab = target / (2 * p.coltiles);
   int64_t max_slab = S / ((int64_t)p.R * 4);
   if (nslab > max_slab) nslab = max_slab;
   if (nslab < 1) nslab = 1;
@@ -59,7 +64,11 @@ __device__ __forceinline__ void reduce_over_y(const float (&vals)[NV], float* sm
   }
 }
 
-// partial[((n*nslab + slab)*2 + which)*C + c] : which 0 = sum x, 1 = sum x^2
+// Statistics are accumulated as SHIFTED sums around a per-(n, c) pivot p = x[n, voxel 0, c]:
+//   partial[((n*(nslab+1) + slab)*2 + which)*C + c] : which 0 = sum (x - p), 1 = sum (x - p)^2 ; row slab = nslab holds p.
+// E[x^2] - mean^2 on raw sums cancels catastrophically in fp32 when |mean| >> std (un-normalised CT intensities reach the
+// first GroupNorm of the 'gcr' order, components.py:45-57); with the pivot the sums stay at the scale of the spread and
+// the result matches torch's Welford-based GroupNorm.
 template <typename T, int V>
 __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int64_t S, int C,
                                   int ncol, int64_t rows_per_slab, int nslab) {
@@ -73,8 +82,16 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
 #pragma unroll
   for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
   const bool active = col < ncol;
+  float* out = partial + ((int64_t)n * (nslab + 1) + slab) * 2 * C;
   if (active) {
     const T* base = x + (int64_t)n * S * C + (int64_t)col * V;
+    float pv[V];
+    load_vec<T, V>(base, pv);
+    if (slab == 0 && threadIdx.y == 0) {
+      float* prow = partial + ((int64_t)n * (nslab + 1) + nslab) * 2 * C + col * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) prow[i] = pv[i];
+    }
     const int64_t R = blockDim.y;
     for (int64_t r = r0 + threadIdx.y; r < r1; r += USTD * R) {      // USTD independent 16-byte loads in flight per thread
       typename RawVec<sizeof(T) * V>::type raw[USTD];
@@ -88,16 +105,60 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
           cvt_raw<T, V>(raw[u], v);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            acc[i] += v[i];
-            acc[V + i] += v[i] * v[i];
+            const float d = v[i] - pv[i];
+            acc[i] += d;
+            acc[V + i] += d * d;
           }
         }
     }
   }
-  float* out = partial + ((int64_t)n * nslab + slab) * 2 * C;
   reduce_over_y<2 * V>(acc, sm, [&](int i, float total) {
     if (active) out[(i / V) * C + col * V + (i % V)] = total;
   });
+}
+
+// Group statistics from per-channel shifted sums (fixed order, double): channel c with pivot p_c, weight w (voxels each
+// partial element stands for), s_c = sum (x - p_c), q_c = sum (x - p_c)^2 over its S values:
+//   mean_c = p_c + s_c / S,  M2_c = q_c - s_c^2 / S;   group: mu = avg_c mean_c,  var = avg_c [M2_c / S + (mean_c - mu)^2]
+// One warp per channel sums the slabs; sh[0..cpg) = mean_c, sh[cpg..2cpg) = M2_c / S.  Returns (mu, var) in thread 0.
+struct ChanSrc {
+  const float* partial;   // [n][nslab + 1][2][C_src]
+  int nslab, C_src, c0;   // group channels [c0_group, ...) map to source channels c - c0
+  double weight;
+};
+__device__ __forceinline__ void channel_moments(const ChanSrc& src, int n, int c_src, double S, int lane, double& mean_c,
+                                                double& var_c) {
+  const float* base = src.partial + (int64_t)n * (src.nslab + 1) * 2 * src.C_src;
+  double s = 0.0, q = 0.0;
+  for (int slab = lane; slab < src.nslab; slab += 32) {
+    s += (double)base[(int64_t)slab * 2 * src.C_src + c_src];
+    q += (double)base[(int64_t)slab * 2 * src.C_src + src.C_src + c_src];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  s *= src.weight;
+  q *= src.weight;
+  const double pivot = (double)base[(int64_t)src.nslab * 2 * src.C_src + c_src];
+  mean_c = pivot + s / S;
+  var_c = q / S - (s / S) * (s / S);
+  if (var_c < 0.0) var_c = 0.0;
+}
+__device__ __forceinline__ void group_stats_finish(double* sh, int cpg, double* scratch, double& mu, double& var) {
+  __syncthreads();
+  double a = 0.0;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) a += sh[i];
+  a = block_sum(a, scratch);
+  __shared__ double s_mu;
+  if (threadIdx.x == 0) s_mu = a / (double)cpg;
+  __syncthreads();
+  mu = s_mu;
+  double b = 0.0;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) b += sh[cpg + i] + (sh[i] - mu) * (sh[i] - mu);
+  b = block_sum(b, scratch);
+  var = b / (double)cpg;
 }
 
 // one block per (n, g): mean / rstd and the per-(n,c) affine table ab[n][0][c] = a, ab[n][1][c] = b
@@ -105,24 +166,21 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const floa
                                    const float* __restrict__ beta, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ ab, int64_t S, int C, int G,
                                    int nslab, float eps) {
+  extern __shared__ double sh_gn[];                  // [2 * cpg]
   __shared__ double scratch[32];
   __shared__ float s_mean, s_rstd;
   const int n = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
-  double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < nslab * cpg; i += blockDim.x) {
-    const int slab = i / cpg, c = g * cpg + i % cpg;
-    const float* p = partial + ((int64_t)n * nslab + slab) * 2 * C;
-    s += (double)p[c];
-    q += (double)p[C + c];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const ChanSrc src{partial, nslab, C, 0, 1.0};
+  for (int i = warp; i < cpg; i += nwarps) {
+    double m, v;
+    channel_moments(src, n, g * cpg + i, (double)S, lane, m, v);
+    if (lane == 0) { sh_gn[i] = m; sh_gn[cpg + i] = v; }
   }
-  s = block_sum(s, scratch);
-  q = block_sum(q, scratch);
+  double mu, var;
+  group_stats_finish(sh_gn, cpg, scratch, mu, var);
   if (threadIdx.x == 0) {
-    const double m = (double)cpg * (double)S;
-    const double mu = s / m;
-    double var = q / m - mu * mu;
-    if (var < 0.0) var = 0.0;
     s_mean = (float)mu;
     s_rstd = (float)(1.0 / sqrt(var + (double)eps));
     mean[n * G + g] = s_mean;
@@ -395,33 +453,24 @@ __global__ void upcat_gn_finalize_kernel(const float* __restrict__ pa, const flo
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ ab,
                                          int64_t S, int Cs, int Cl, int G, int nslab_a, int nslab_b, float eps) {
+  extern __shared__ double sh_gn[];                  // [2 * cpg]
   __shared__ double scratch[32];
   __shared__ float s_mean, s_rstd;
   const int n = blockIdx.x / G, g = blockIdx.x % G;
   const int C = Cs + Cl, cpg = C / G;
-  const int nslab = nslab_a > nslab_b ? nslab_a : nslab_b;
-  double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < nslab * cpg; i += blockDim.x) {
-    const int slab = i / cpg, c = g * cpg + i % cpg;
-    if (c < Cs) {
-      if (slab < nslab_a) {
-        const float* p = pa + ((int64_t)n * nslab_a + slab) * 2 * Cs;
-        s += (double)p[c];
-        q += (double)p[Cs + c];
-      }
-    } else if (slab < nslab_b) {
-      const float* p = pb + ((int64_t)n * nslab_b + slab) * 2 * Cl;
-      s += 8.0 * (double)p[c - Cs];
-      q += 8.0 * (double)p[Cl + c - Cs];
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const ChanSrc sa{pa, nslab_a, Cs, 0, 1.0};
+  const ChanSrc sb{pb, nslab_b, Cl, Cs, 8.0};       // every low-resolution voxel appears 8 times in the upsampled concat
+  for (int i = warp; i < cpg; i += nwarps) {
+    const int c = g * cpg + i;
+    double m, v;
+    if (c < Cs) channel_moments(sa, n, c, (double)S, lane, m, v);
+    else channel_moments(sb, n, c - Cs, (double)S, lane, m, v);
+    if (lane == 0) { sh_gn[i] = m; sh_gn[cpg + i] = v; }
   }
-  s = block_sum(s, scratch);
-  q = block_sum(q, scratch);
+  double mu, var;
+  group_stats_finish(sh_gn, cpg, scratch, mu, var);
   if (threadIdx.x == 0) {
-    const double m = (double)cpg * (double)S;
-    const double mu = s / m;
-    double var = q / m - mu * mu;
-    if (var < 0.0) var = 0.0;
     s_mean = (float)mu;
     s_rstd = (float)(1.0 / sqrt(var + (double)eps));
     mean[n * G + g] = s_mean;
@@ -630,7 +679,7 @@ using namespace mednet;
 extern "C" size_t mednet_groupnorm_fwd_workspace_bytes(const mednet_gn_fwd_params* p) {
   if (!p || !dtype_ok(p->dtype) || p->C <= 0) return 0;
   SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
-  return align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256) +
+  return align_up((size_t)p->N * (pl.nslab + 1) * 2 * p->C * sizeof(float), 256) +
          align_up((size_t)p->N * 2 * p->C * sizeof(float), 256);
 }
 
@@ -643,7 +692,7 @@ extern "C" int mednet_groupnorm_fwd(const mednet_gn_fwd_params* p, void* workspa
   MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_groupnorm_fwd_workspace_bytes(p), MEDNET_EWORKSPACE);
   SlabPlan pl = make_plan(p->N, p->S, p->C, dtype_bytes(p->dtype));
   float* partial = (float*)workspace;
-  float* ab = (float*)((char*)workspace + align_up((size_t)p->N * pl.nslab * 2 * p->C * sizeof(float), 256));
+  float* ab = (float*)((char*)workspace + align_up((size_t)p->N * (pl.nslab + 1) * 2 * p->C * sizeof(float), 256));
   dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
   MEDNET_DISPATCH_TV(p->dtype, pl.V, {
     size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
@@ -651,8 +700,8 @@ extern "C" int mednet_groupnorm_fwd(const mednet_gn_fwd_params* p, void* workspa
                                                             pl.rows_per_slab, pl.nslab);
   });
   MEDNET_LAUNCH_CHECK();
-  gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(partial, p->gamma, p->beta, p->mean, p->rstd, ab,
-                                                                  p->S, p->C, p->G, pl.nslab, p->eps);
+  gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 2 * (p->C / p->G) * sizeof(double), stream>>>(
+      partial, p->gamma, p->beta, p->mean, p->rstd, ab, p->S, p->C, p->G, pl.nslab, p->eps);
   MEDNET_LAUNCH_CHECK();
   MEDNET_DISPATCH_TV(p->dtype, pl.V, {
     gn_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->residual, (T*)p->y, ab, p->S,
@@ -756,8 +805,8 @@ UpcatPlan upcat_plan(int N, int D, int H, int W, int Cs, int Cl, int dtype) {
   u.pa = make_plan(N, S, Cs, eb);
   u.pb = make_plan(N, S / 8, Cl, eb);
   u.pc = make_plan(N, (int64_t)D * H, Cs + Cl, eb, u.V, 12);   // slabs of (z, y) LINES of W voxels (concat-grid kernels)
-  u.pa_bytes = align_up((size_t)N * u.pa.nslab * 2 * Cs * sizeof(float), 256);
-  u.pb_bytes = align_up((size_t)N * u.pb.nslab * 2 * Cl * sizeof(float), 256);
+  u.pa_bytes = align_up((size_t)N * (u.pa.nslab + 1) * 2 * Cs * sizeof(float), 256);
+  u.pb_bytes = align_up((size_t)N * (u.pb.nslab + 1) * 2 * Cl * sizeof(float), 256);
   return u;
 }
 }  // namespace
@@ -800,8 +849,8 @@ extern "C" int mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, v
     });
     MEDNET_LAUNCH_CHECK();
   }
-  upcat_gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(pa, pb, p->gamma, p->beta, p->mean, p->rstd, ab, S,
-                                                                        p->Cs, p->Cl, p->G, u.pa.nslab, u.pb.nslab, p->eps);
+  upcat_gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 2 * ((p->Cs + p->Cl) / p->G) * sizeof(double), stream>>>(
+      pa, pb, p->gamma, p->beta, p->mean, p->rstd, ab, S, p->Cs, p->Cl, p->G, u.pa.nslab, u.pb.nslab, p->eps);
   MEDNET_LAUNCH_CHECK();
   {
     const SlabPlan& pl = u.pc;

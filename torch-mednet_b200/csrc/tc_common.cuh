@@ -42,12 +42,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (fails the launch) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (fails the launch) instead of hanging the GPU.  The bound is ~20 s of SM clocks
+// (4e10 cycles at <= 2 GHz): far beyond any legitimate wait -- including a kernel that is time-sliced with another
+// process or pre-empted under MPS, where the SM clock keeps counting while the CTA is descheduled -- yet it still turns a
+// dead-locked pipeline into a reported launch failure instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > 40000000000LL) {
       printf("mednet tcgen05: mbarrier timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -175,13 +175,6 @@ def k_intensity_augment(x, coef, dst_dtype):
     return y
 
 
-# in_channels < 16 (the 1-channel image) can be zero-padded to 16 channels to run the first layer on the tensor-core
-# kernels (set to 16).  Measured on cfg-3 (profiles/r01j_first_layer_pad.txt): K = 16 leaves 2 MMAs per tap and issuer,
-# so the launches are latency-bound (2.3 ms each for fprop / dgrad, 1.9 ms wgrad) and the step is 1.1 ms SLOWER than with
-# the register-tiled CUDA-core stencil kernels (1.5 / 1.7 / 1.9 ms) -> off by default.
-FIRST_LAYER_PAD = 0
-
-
 def conv_select_impl(x_shape, out_sp, K, Nout, dtype, gather, impl, x_ptr=0, w_ptr=0, y_ptr=0):
     n, di, hi, wi = x_shape[0], x_shape[1], x_shape[2], x_shape[3]
     if dtype == torch.bfloat16 and impl != "simt":
@@ -668,31 +661,20 @@ class Conv3x3Fn(torch.autograd.Function):
         x = _c(x)
         cout, cin = weight.shape[0], weight.shape[1]
         sp = tuple(x.shape[1:4])
-        ctx.cin_real = cin
-        weight_eff = weight
-        if FIRST_LAYER_PAD and cin < FIRST_LAYER_PAD and x.dtype == torch.bfloat16 and impl != "simt" and cout % 16 == 0:
-            padded_shape = tuple(x.shape[:-1]) + (FIRST_LAYER_PAD,)
-            if conv_select_impl(padded_shape, sp, FIRST_LAYER_PAD, cout, x.dtype, 0, impl) == 2:
-                # few input channels (the image): zero-pad activations and weights to 16 channels -> tensor cores for
-                # fprop, dgrad (cut back to the real channels) and wgrad instead of the CUDA-core stencil kernels
-                x = k_channel_pad(x, FIRST_LAYER_PAD)
-                w16 = weight.new_zeros((cout, FIRST_LAYER_PAD, 3, 3, 3))
-                w16[:, :cin] = weight.detach()
-                weight_eff, cin = w16, FIRST_LAYER_PAD
         impl_id = conv_select_impl(x.shape, sp, cin, cout, x.dtype, 0, impl, x.data_ptr(), 0, 0)
-        wp = k_pack_weights(weight_eff, cin, cout, x.dtype, 2 if impl_id == 2 else 0)
+        wp = k_pack_weights(weight, cin, cout, x.dtype, 2 if impl_id == 2 else 0)
         add = _c(addend) if addend is not None else None
         y = k_conv3(x, wp, cout, sp, 0, impl_id, bias=bias.detach().float() if bias is not None else None,
                     addend=add, act=act)
         bwd_act = 0 if defer_act else act
         ctx.weight_ref = weight                      # the Parameter itself (its .grad buffer may be written asynchronously)
-        ctx.save_for_backward(x, weight_eff, y if bwd_act else None)
+        ctx.save_for_backward(x, weight, y if bwd_act else None)
         ctx.act, ctx.impl, ctx.has_bias, ctx.has_addend = bwd_act, impl, bias is not None, addend is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors            # x / weight are the 16-channel padded versions for a padded first layer
+        x, weight, y = ctx.saved_tensors
         dy = _c(dy)
         cout, cin = weight.shape[0], weight.shape[1]
         dpre = k_act_bwd(y, dy, ctx.act) if ctx.act else dy
@@ -702,16 +684,12 @@ class Conv3x3Fn(torch.autograd.Function):
             impl_id = conv_select_impl(dpre.shape, sp, cout, cin, dpre.dtype, 0, ctx.impl, dpre.data_ptr(), 0, 0)
             wp = k_pack_weights(weight, cin, cout, dpre.dtype, 3 if impl_id == 2 else 1)
             dx = k_conv3(dpre, wp, cin, sp, 0, impl_id)
-            if cin != ctx.cin_real:
-                dx = k_channel_pad(dx, ctx.cin_real)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             wimpl = "simt" if ctx.impl == "simt" else "auto"
-            if not ctx.has_bias and cin == ctx.cin_real and _async_wgrad_ok(ctx.weight_ref):
+            if not ctx.has_bias and _async_wgrad_ok(ctx.weight_ref):
                 wgrad_async(dpre, x, 0, wimpl, ctx.weight_ref)       # overlaps the rest of backward; dw stays None
             else:
                 dw, db = k_wgrad(dpre, x, 0, wimpl, want_bias=ctx.has_bias)
-                if cin != ctx.cin_real:
-                    dw = dw[:, :ctx.cin_real].contiguous()
         return dx, dw, db, (dpre if ctx.has_addend else None), None, None, None
 
 
