@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* mednet_stream_t;
 
-#define MEDNET_ABI_VERSION 2
+#define MEDNET_ABI_VERSION 3
 
 /* dtypes */
 #define MEDNET_F32  0
@@ -370,6 +370,29 @@ int mednet_predict_epilogue(const mednet_predict_params* p, mednet_stream_t stre
  * ref: mm/unet/model.py:79-82,107-108. */
 int mednet_final_activation(const float* logits, float* out, int64_t N, int64_t S, int32_t C, int32_t sigmoid,
                             mednet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm affine -> 3x3x3 conv on a tensor that needs NO gradient (the image: first layer of the 'gcr' networks,
+ * mm/unet/components.py:45-57 then :8-9).  The conv's input gradient would only feed the two per-channel sums of the
+ * GroupNorm backward; the adjoint identity <dgrad(dpre), u> = <dpre, conv(u)> yields them from the weight gradient taken
+ * against the normalised input xhat (ghat) and from border-class sums of dpre, so neither the dgrad nor the GroupNorm
+ * backward of that layer is launched (csrc/input_affine.cu has the algebra).
+ *   mednet_border_class_sums: bins[((a*3+b)*3+c)][C] = sum of x over the voxels of class a / b / c along d / h / w
+ *     (0 interior, 1 first plane, 2 last plane), over the whole batch.  D, H, W >= 2.
+ *   mednet_conv3d_affine_input_grads: dw = gamma*ghat + beta*B, dgamma = sum w*ghat, dbeta = sum w*B with
+ *     B[co][t] = sum of the bins whose voxels see tap t inside the volume; `dtype` BF16 rounds w as the conv did.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; float* bins; int32_t N, D, H, W, C, dtype;
+} mednet_border_sums_params;
+size_t mednet_border_class_sums_workspace_bytes(const mednet_border_sums_params* p);
+int    mednet_border_class_sums(const mednet_border_sums_params* p, void* workspace, size_t workspace_bytes,
+                                mednet_stream_t stream);
+typedef struct {
+  const float* w; const float* ghat; const float* bins; const float* gamma; const float* beta;
+  float* dw; float* dgamma; float* dbeta; int32_t Cout, Cin, dtype;
+} mednet_affine_input_params;
+int mednet_conv3d_affine_input_grads(const mednet_affine_input_params* p, mednet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused Adam on a flat fp32 parameter bucket (PyTorch defaults: no weight decay, no amsgrad).

@@ -174,7 +174,15 @@ def layerwise_report(net, x, y, weight, f_maps):
 
     def param_rows(prefix, mod):
         for pname, p in mod.named_parameters():
-            add(prefix, "d" + pname, p.grad.float(), o["grads"][prefix + pname], rounded=False)
+            got, want = p.grad.float(), o["grads"][prefix + pname]
+            if want.numel() < 8 and pname == "groupnorm.weight" and hasattr(mod, "conv"):
+                # A handful of numbers that are ~0 by construction: the next GroupNorm makes the loss invariant to the
+                # scale of this layer's (ReLU) output, so dgamma = sum_v dxn * xhat = sum W (.) dW cancels to ~1e-5 of its
+                # terms.  Its error is measured against the size of those terms (Cauchy-Schwarz bound ||W|| ||dW||).
+                scale = (mod.conv.weight.detach().float().norm() * o["grads"][prefix + "conv.weight"].norm()).item()
+                rows.append((prefix, "d" + pname + " /|W||dW|", (got - want).norm().item() / scale, 1.0))
+            else:
+                add(prefix, "d" + pname, got, want, rounded=False)
             p.grad = None
 
     after_pool = False

@@ -467,3 +467,35 @@ def test_groupnorm_large_offset_input_matches_welford(c, groups):
         ref2 = F.group_norm(cat, groups, g2, b2, eps=1e-5)
         y2 = ops.UpcatGroupNormFn.apply(ndhwc(skip), ndhwc(low), g2.to(DEV), b2.to(DEV), groups, 0, 0)
         assert relerr(ncdhw(y2), ref2) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,groups,shape", [(1, 32, 1, (6, 9, 20)), (1, 16, 1, (2, 2, 2)), (2, 8, 1, (5, 4, 7)),
+                                                   (4, 64, 2, (3, 6, 5))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_first_layer_without_data_gradient(cin, cout, groups, shape, dtype):
+    """GroupNorm -> conv -> ReLU on the image (no input gradient): dgamma / dbeta / dW from the adjoint identity
+    (ops.NormConvInputFn: no dgrad, no GroupNorm backward) against torch autograd of the reference ops
+    (components.py:45-57, :8-9), with perturbed affine parameters and every border class populated."""
+    torch.manual_seed(cin + cout)
+    q = (lambda t: t.to(dtype).float()) if dtype == torch.bfloat16 else (lambda t: t)
+    x = q(torch.randn(2, cin, *shape) * 2.0 + 3.0)                 # the image as the network stores it
+    gamma = (torch.rand(cin) + 0.5).requires_grad_()
+    beta = (torch.randn(cin) * 0.5).requires_grad_()
+    w = (torch.randn(cout, cin, 3, 3, 3) * 0.2).requires_grad_()
+    xn = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    xn_q = xn + (q(xn) - xn).detach()                              # stored in the compute dtype, fp32 gradient
+    wq = w + (q(w) - w).detach()
+    ref = F.relu(F.conv3d(xn_q, wq, None, padding=1))
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    xg = ndhwc(x, dtype)
+    assert not xg.requires_grad
+    gd, bd, wd = (t.detach().to(DEV).requires_grad_() for t in (gamma, beta, w))
+    assert ops.norm_conv_input_supported(xg, wd, None)
+    y = ops.NormConvInputFn.apply(xg, gd, bd, groups, wd, 1, "auto")
+    y.backward(ndhwc(g, dtype))
+    tol, gtol = (2e-5, 2e-5) if dtype == torch.float32 else (6e-3, 2e-2)     # bf16: one rounding of xhat vs of xn per voxel
+    assert relerr(ncdhw(y.detach()), ref.detach()) < tol
+    assert relerr(wd.grad.cpu(), w.grad) < gtol
+    assert relerr(gd.grad.cpu(), gamma.grad) < gtol
+    assert relerr(bd.grad.cpu(), beta.grad) < gtol

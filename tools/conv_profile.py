@@ -60,6 +60,44 @@ def main():
                               epi_wait_acc=f(5, epi), halo_prod_wait=f(6, tot), w_prod_wait=f(7, tot),
                               clk_ghz=round(tot / (ms * 1e6), 3))))
     check(lib().mednet_tcgen05_set_option(b"conv_profile", 0), "set_option")
+    # ---- weight gradient: share of the MMA issuer's cycles spent waiting for a TMA-filled stage, per layer
+    for cin, cout, div in LAYERS:
+        if cin == 64 and cout in (192, 32):
+            continue
+        s = a.edge // div
+        x = torch.randn(a.batch, s, s, s, cin, device="cuda").to(torch.bfloat16)
+        dy = torch.randn(a.batch, s, s, s, cout, device="cuda").to(torch.bfloat16)
+        dw = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device="cuda")
+        p = ops.wgrad_params(dy, x, 0, "tcgen05", dw, None)
+        check(lib().mednet_tcgen05_set_option(b"wgrad_profile", 1), "set_option")
+        nbytes = lib().mednet_conv3d_wgrad_workspace_bytes(_abi.C.byref(p))
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        check(lib().mednet_tcgen05_set_option(b"wgrad_profile", 0), "set_option")
+        for _ in range(2):
+            check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), ws.data_ptr(), nbytes, ops._stream()), "wgrad")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), ws.data_ptr(), nbytes, ops._stream()), "wgrad")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        check(lib().mednet_tcgen05_set_option(b"wgrad_profile", 1), "set_option")
+        ws[nbytes - 65536:].zero_()
+        check(lib().mednet_conv3d_wgrad(_abi.C.byref(p), ws.data_ptr(), nbytes, ops._stream()), "wgrad")
+        torch.cuda.synchronize()
+        check(lib().mednet_tcgen05_set_option(b"wgrad_profile", 0), "set_option")
+        c = ws[nbytes - 65536:].view(torch.int64).view(2, 1024, 4).double()
+        flops = 2.0 * a.batch * s ** 3 * cin * cout * 27
+        row = dict(layer=f"{cin}->{cout}@{s}^3", op="wgrad", ms=round(ms, 3), tflops=round(flops / ms / 1e9, 1))
+        for seg in range(2):
+            cs = c[seg][c[seg][:, 0] > 0]
+            if len(cs):
+                row[f"seg{seg}"] = dict(ctas=len(cs), mma_cycles=int(cs[:, 0].mean()), max_cycles=int(cs[:, 0].max()),
+                                        wait_stage=round((cs[:, 1].mean() / cs[:, 0].mean()).item(), 3),
+                                        producer_wait=round((cs[:, 2].mean() / cs[:, 0].mean()).item(), 3),
+                                        bricks=cs[:, 3].mean().item(),
+                                        clk_per_brick=int((cs[:, 0].sum() / cs[:, 3].sum()).item()))
+        print(json.dumps(row))
 
 
 if __name__ == "__main__":

@@ -33,6 +33,7 @@ namespace {
 int g_pair_planes = 1;        // mednet_tcgen05_set_option("wgrad_pair_planes", 0|1)
 int g_d_fastest = 1;          // mednet_tcgen05_set_option("wgrad_d_fastest", 0|1)
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
+int g_profile = 0;            // mednet_tcgen05_set_option("wgrad_profile", 0|1): wait-cycle counters, see wgrad_tc_kernel<PROF>
 
 constexpr int WG_THREADS = 192;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue
 constexpr int BR_H = 16, BR_W = 8;       // brick (h, w); depth TD
@@ -62,9 +63,32 @@ struct WgArgs {
   float* partial;              // [ksplit][worktype][128][PART_COLS]
 };
 
+// MMAs of one staged brick for the tap-group slots [GB, GE): TD planes x 8 pairs of h rows x (GE - GB) groups, straight-line
+// (per-MMA predicates cost the issuing thread ~8 uniform-register moves each, taken or not: the group range is a template
+// parameter and the per-brick choice is made once, outside)
+template <int GB, int GE>
+__device__ __forceinline__ void wg_issue_brick(int TD, uint32_t a_st, uint32_t b_st, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                               const uint32_t (&tmem_g)[5], const uint32_t (&goff)[5], uint32_t a_dz16,
+                                               uint32_t b_dz16, uint32_t a_hp16, uint32_t b_hp16) {
+  for (int dz = 0; dz < TD; ++dz) {
+    uint32_t a_lo = a_st + (uint32_t)dz * a_dz16, b_lo = b_st + (uint32_t)dz * b_dz16;
+#pragma unroll
+    for (int hp = 0; hp < 8; ++hp) {
+#pragma unroll
+      for (int g = GB; g < GE; ++g) tc::umma_bf16_lohi(tmem_g[g], a_lo, a_hi, b_lo + goff[g], b_hi, idesc, 1u);
+      a_lo += a_hp16;
+      b_lo += b_hp16;
+    }
+  }
+}
+
+// PROF: per-CTA cycle counters prof_out[blockIdx.x * 4 + i]: 0 MMA issuer total, 1 its wait for a filled stage,
+// 2 TMA producer wait for a free stage, 3 bricks processed
+template <bool PROF>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_s,
-                const __grid_constant__ CUtensorMap map_u2, const WgArgs p) {
+                const __grid_constant__ CUtensorMap map_u2, const WgArgs p, long long* __restrict__ prof_out) {
+  long long* prof = PROF ? prof_out + (size_t)blockIdx.x * 4 : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int u_atom_bytes = p.TD * 128 * 128;                       // one 64-channel atom of the brick
@@ -130,11 +154,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (shared_slot >= 0) {
-    // the shared slot may not be touched by this CTA's first brick: clear it, then every MMA into it accumulates
+  {
+    // every accumulator slot starts at zero, so every MMA accumulates: no first-MMA special case in the issue loop, and the
+    // shared slot (which this CTA's first brick may not touch) needs no separate treatment
     if (warp >= 2) {
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(shared_slot * NCOLS);
-      for (int j = 0; j < NCOLS; j += 16) tc::tmem_st_x16_zero(taddr + (uint32_t)j);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int j = 0; j < ngroups * NCOLS; j += 16) tc::tmem_st_x16_zero(taddr + (uint32_t)j);
       tc::tmem_st_wait();
     }
     tc::tc_fence_before();
@@ -146,6 +171,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
       uint32_t it = 0;
+      long long w_empty = 0;
       for (int64_t b = b_begin; b < b_end; ++b, ++it) {
         const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
         int64_t t = b;
@@ -163,7 +189,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
           d0 = (int)(t % tiles_d) * p.TD - (paired ? p.TD : 0);
           n = (int)(t / tiles_d);
         }
-        tc::mbar_wait(&empty[st], ph ^ 1u);
+        if (PROF) { const long long t0 = clock64(); tc::mbar_wait(&empty[st], ph ^ 1u); w_empty += clock64() - t0; }
+        else tc::mbar_wait(&empty[st], ph ^ 1u);
         uint8_t* dst = smem + (size_t)st * stage_bytes;
         if (paired) {
           tc::mbar_arrive_expect_tx(&full[st], (uint32_t)((p.TD + 1) * 128 * 128 + s_bytes_raw));
@@ -180,6 +207,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         tc::tma_load_5d(dst + u_bytes, &map_s, &full[st], sc * CS, ss * (w0 - 1) + spw, ss * (h0 - 1) + sph,
                         ss * (d0 - 1) + spd, n);
       }
+      if (PROF) prof[2] = w_empty;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -194,42 +222,62 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W) * (2 * CS)) >> 4;
       }
       const uint32_t s_base = tc::smem_u32(smem);
+      // A: MN-major, 128-byte rows, atoms u_atom_bytes apart (paired mode: the same channels one 16 KB d-plane further),
+      //    8-row groups 1024 B apart.  B: MN-major, 64-byte rows, three chained windows one row (64 B) apart, 8-row
+      //    groups = next halo row.
+      const uint64_t da0 = tc::make_smem_desc(s_base, paired ? 128u * 128u : (uint32_t)u_atom_bytes, 1024u, 0, tc::SWZ_128B);
+      const uint64_t db0 = tc::make_smem_desc(s_base + (uint32_t)u_bytes, (uint32_t)(2 * CS), (uint32_t)(HL_W * 2 * CS), 0,
+                                              tc::SWZ_64B);
+      const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)da0, b_lo0 = (uint32_t)db0;
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_dz16 = (128u * 128u) >> 4, b_dz16 = (uint32_t)(HL_H * HL_W * 2 * CS) >> 4;
+      const uint32_t a_hp16 = (16u * 128u) >> 4, b_hp16 = (uint32_t)(2 * HL_W * 2 * CS) >> 4;
+      uint32_t tmem_g[GROUPS0];
+      uint32_t base_mask = 0;
+#pragma unroll
+      for (int g = 0; g < GROUPS0; ++g) {
+        tmem_g[g] = tmem_base + (uint32_t)(g * NCOLS);
+        if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u))) base_mask |= 1u << g;
+      }
+      const uint32_t shared_bit = shared_slot >= 0 ? (1u << shared_slot) : 0u;
       uint32_t it = 0;
+      long long w_full = 0;
+      const long long t_begin = PROF ? clock64() : 0;
       for (int64_t b = b_begin; b < b_end; ++b, ++it) {
         const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
-        tc::mbar_wait(&full[st], ph);
+        if (PROF) { const long long t0 = clock64(); tc::mbar_wait(&full[st], ph); w_full += clock64() - t0; }
+        else tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
-        const uint32_t u_addr = s_base + st * (uint32_t)stage_bytes;
-        // A: MN-major, 128-byte rows, atoms u_atom_bytes apart, 8-row groups 1024 B apart
-        const uint64_t da0 = tc::make_smem_desc(u_addr, paired ? 128u * 128u : (uint32_t)u_atom_bytes, 1024u, 0, tc::SWZ_128B);
-        // B: MN-major, 64-byte rows, three chained windows one row (64 B) apart, 8-row groups = next halo row
-        const uint64_t db0 = tc::make_smem_desc(u_addr + (uint32_t)u_bytes, (uint32_t)(2 * CS), (uint32_t)(HL_W * 2 * CS), 0,
-                                                tc::SWZ_64B);
-        uint32_t acc = it != 0 ? 1u : 0u;
+        // The issuing thread is a serial instruction stream (~55 clk per tcgen05.mma at best): descriptors are built once
+        // per kernel, per MMA only 32-bit address words are advanced, and which tap groups this brick feeds is one
+        // bit mask evaluated per brick, not per MMA.
+        const uint32_t a_st = a_lo0 + st * stage16, b_st = b_lo0 + st * stage16;
         const bool shared_mine = (int)(b & 1) == role;          // which role computes the shared group for this brick
-        for (int dz = 0; dz < p.TD; ++dz) {
-          const uint64_t da_z = da0 + (uint64_t)((dz * 128 * 128) >> 4);
-          const uint64_t db_z = db0 + (uint64_t)((dz * HL_H * HL_W * 2 * CS) >> 4);
+        if (paired) {
+          wg_issue_brick<0, 3>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+        } else if (base_mask == 0x1fu) {
+          if (shared_mine) wg_issue_brick<0, 5>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+          else if (role == 0) wg_issue_brick<0, 4>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+          else wg_issue_brick<1, 5>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+        } else {
+          // transposed-conv parity classes: only the tap groups of gmask (at most 4 of 9), rare and small launches
+          const uint32_t act = shared_mine ? base_mask : (base_mask & ~shared_bit);
+          for (int dz = 0; dz < p.TD; ++dz) {
+            uint32_t a_lo = a_st + (uint32_t)dz * a_dz16, b_lo = b_st + (uint32_t)dz * b_dz16;
+            for (int hp = 0; hp < 8; ++hp) {
 #pragma unroll
-          for (int hp = 0; hp < 8; ++hp) {
-            const uint64_t da = da_z + (uint64_t)((hp * 16 * 128) >> 4);
-            const uint64_t db = db_z + (uint64_t)((hp * 2 * HL_W * 2 * CS) >> 4);
-#pragma unroll
-            for (int g = 0; g < GROUPS0; ++g) {
-              if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u))) {
-                if (g == shared_slot) {
-                  if (shared_mine) tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, 1u);
-                } else {
-                  tc::umma_bf16(tmem_base + (uint32_t)(g * NCOLS), da, db + goff[g], idesc, acc);
-                }
-              }
+              for (int g = 0; g < GROUPS0; ++g)
+                if ((act >> g) & 1u) tc::umma_bf16_lohi(tmem_g[g], a_lo, a_hi, b_lo + goff[g], b_hi, idesc, 1u);
+              a_lo += a_hp16;
+              b_lo += b_hp16;
             }
-            acc = 1u;
           }
         }
         tc::umma_commit(&empty[st]);
       }
       tc::umma_commit(done);
+      if (PROF) { tc::mbar_wait(done, 0); prof[0] = clock64() - t_begin; prof[1] = w_full; prof[3] = b_end - b_begin; }
     }
   } else {
     // ===================== epilogue (once per CTA) =====================
@@ -380,6 +428,12 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
 void tc_wgrad_set_wt_fastest(int v) { g_wt_fastest = v ? 1 : 0; }
 void tc_wgrad_set_pair_planes(int v) { g_pair_planes = v ? 1 : 0; }
 void tc_wgrad_set_d_fastest(int v) { g_d_fastest = v ? 1 : 0; }
+void tc_wgrad_set_profile(int v) { g_profile = v ? 1 : 0; }
+size_t tc_wgrad_profile_offset(const mednet_wgrad_params* q) {
+  WgPlan pl;
+  if (!plan_wgrad(q, &pl)) return 0;
+  return pl.partial_bytes + colsum_workspace_bytes(q);
+}
 
 bool tc_wgrad_supported(const mednet_wgrad_params* q) {
   WgPlan pl;
@@ -389,7 +443,7 @@ bool tc_wgrad_supported(const mednet_wgrad_params* q) {
 size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params* q) {
   WgPlan pl;
   if (!plan_wgrad(q, &pl)) return 0;
-  return pl.partial_bytes + colsum_workspace_bytes(q);
+  return pl.partial_bytes + colsum_workspace_bytes(q) + (g_profile ? 2 * 4 * 1024 * sizeof(long long) : 0);
 }
 
 int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
@@ -447,7 +501,9 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> lock(mu);
     if (pl.smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
       if (e != cudaSuccess) return (int)e;
       configured = pl.smem;
     }
@@ -462,7 +518,11 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
       const WgSeg& sg = pl.seg[i];
       a.ut_base = sg.ut_base; a.u_tiles = sg.u_tiles; a.ksplit = sg.ksplit;
       a.partial = (float*)workspace + sg.offset_floats;
-      wgrad_tc_kernel<<<(unsigned)sg.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, map_u2, a);
+      if (g_profile)     // counters of segment i behind the partial sums and the bias scratch (workspace sized for it)
+        wgrad_tc_kernel<true><<<(unsigned)sg.grid, WG_THREADS, pl.smem, st>>>(
+            map_u, map_s, map_u2, a, (long long*)((char*)workspace + pl.partial_bytes + colsum_workspace_bytes(q)) + (size_t)i * 4 * 1024);
+      else
+        wgrad_tc_kernel<false><<<(unsigned)sg.grid, WG_THREADS, pl.smem, st>>>(map_u, map_s, map_u2, a, nullptr);
       MEDNET_LAUNCH_CHECK();
     }
     return MEDNET_OK;

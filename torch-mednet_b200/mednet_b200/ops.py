@@ -323,6 +323,37 @@ def wgrad_async(a, b, gather, impl, weight):
         async_grad_listener(weight)
 
 
+def k_border_class_sums(x):
+    """(27, C) fp32 sums of an NDHWC tensor over the voxels of each border class (include/mednet_b200.h)."""
+    _need_cuda(x)
+    x = _c(x)
+    n, d, h, w, c = x.shape
+    bins = torch.empty((27, c), dtype=torch.float32, device=x.device)
+    p = make("mednet_border_sums_params", x=_ptr(x), bins=_ptr(bins), N=n, D=d, H=h, W=w, C=c, dtype=_dt(x))
+    nbytes = lib().mednet_border_class_sums_workspace_bytes(_abi.C.byref(p))
+    if nbytes == 0:
+        raise _abi.MednetError("border_class_sums: unsupported shape (needs D, H, W >= 2)")
+    ws = _ws(nbytes, x.device)
+    check(lib().mednet_border_class_sums(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "border_class_sums")
+    _count(2)
+    return bins
+
+
+def k_affine_input_grads(weight, ghat, bins, gamma, beta, conv_dtype):
+    """dW, dgamma, dbeta of `conv(gamma * xhat + beta)` from ghat = wgrad(dpre, xhat) and the border-class sums of dpre."""
+    _need_cuda(weight, ghat, bins, gamma, beta)
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().contiguous().float()
+    dw = torch.empty_like(w)
+    dgamma = torch.empty(cin, dtype=torch.float32, device=w.device)
+    dbeta = torch.empty(cin, dtype=torch.float32, device=w.device)
+    p = make("mednet_affine_input_params", w=_ptr(w), ghat=_ptr(ghat), bins=_ptr(bins), gamma=_ptr(gamma), beta=_ptr(beta),
+             dw=_ptr(dw), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta), Cout=cout, Cin=cin, dtype=_DT[conv_dtype])
+    check(lib().mednet_conv3d_affine_input_grads(_abi.C.byref(p), _stream()), "conv3d_affine_input_grads")
+    _count()
+    return dw, dgamma, dbeta
+
+
 def k_conv1_fwd(x, w2d, bias):
     _need_cuda(x, w2d, bias)
     n, sp, cin = x.shape[0], tuple(x.shape[1:-1]), x.shape[-1]
@@ -691,6 +722,45 @@ class Conv3x3Fn(torch.autograd.Function):
             else:
                 dw, db = k_wgrad(dpre, x, 0, wimpl, want_bias=ctx.has_bias)
         return dx, dw, db, (dpre if ctx.has_addend else None), None, None, None
+
+
+def norm_conv_input_supported(x, weight, bias):
+    """GroupNorm -> conv on a tensor that needs no gradient (the image), few input channels, no conv bias."""
+    return (not x.requires_grad and bias is None and weight.shape[1] <= 4 and min(x.shape[1:4]) >= 2 and
+            weight.shape[0] % 8 == 0)
+
+
+class NormConvInputFn(torch.autograd.Function):
+    """GroupNorm -> 3x3x3 conv (+ activation) applied to a tensor that needs NO gradient: the first layer of the 'gcr'
+    networks (components.py:45-57 then :8-9 on the image).  Backward launches neither the convolution's data gradient nor
+    the GroupNorm backward: dgamma / dbeta / dW follow from ONE weight gradient against the normalised input and the
+    border-class sums of the output gradient (adjoint identity, csrc/input_affine.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, weight, act, impl, defer_act=False):
+        x = _c(x)
+        g, b = gamma.detach().float(), beta.detach().float()
+        xn, _mean, _rstd = k_gn_fwd(x, g, b, groups, 0, None)
+        cout, cin = weight.shape[0], weight.shape[1]
+        sp = tuple(x.shape[1:4])
+        impl_id = conv_select_impl(xn.shape, sp, cin, cout, xn.dtype, 0, impl, xn.data_ptr(), 0, 0)
+        wp = k_pack_weights(weight, cin, cout, xn.dtype, 2 if impl_id == 2 else 0)
+        y = k_conv3(xn, wp, cout, sp, 0, impl_id, act=act)
+        bwd_act = 0 if defer_act else act
+        ctx.save_for_backward(x, weight, g, b, y if bwd_act else None)
+        ctx.cfg = (groups, bwd_act, impl)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, g, b, y = ctx.saved_tensors
+        groups, act, impl = ctx.cfg
+        dy = _c(dy)
+        dpre = k_act_bwd(y, dy, act) if act else dy
+        xhat, _m, _r = k_gn_fwd(x, torch.ones_like(g), torch.zeros_like(b), groups, 0, None)   # recomputed: 1-4 channels
+        ghat, _ = k_wgrad(dpre, xhat, 0, "simt" if impl == "simt" else "auto")
+        dw, dgamma, dbeta = k_affine_input_grads(weight, ghat, k_border_class_sums(dpre), g, b, dpre.dtype)
+        return None, dgamma, dbeta, None, dw, None, None, None
 
 
 class ConvTranspose3x3Fn(torch.autograd.Function):

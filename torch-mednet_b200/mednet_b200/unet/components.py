@@ -167,6 +167,13 @@ class SingleConv(nn.Module):
         last = len(self._plan) - 1
         if in_act and not self.accepts_in_act:
             raise RuntimeError("in_act needs a layer that starts with GroupNorm")
+        if (len(self._plan) == 2 and self._plan[0] == ('g', 0) and self._plan[1][0] == 'c' and not skip_first and
+                residual is None and not final_act and not in_act and torch.is_grad_enabled() and
+                ops.norm_conv_input_supported(x, self.conv.weight, self.conv.bias)):
+            # 'g' 'c' [act] on a tensor that needs no gradient (the image): fused first layer, no dgrad / GroupNorm backward
+            gn = self.groupnorm
+            return ops.NormConvInputFn.apply(x, gn.weight, gn.bias, gn.num_groups, self.conv.weight, self._plan[1][1],
+                                             self.cfg.conv_impl, bool(defer and self._plan[1][1]))
         for i, (kind, act) in enumerate(self._plan):
             if i == 0 and skip_first:
                 continue
