@@ -55,11 +55,22 @@ typedef struct CUstream_st* mednet_stream_t;
 #define MEDNET_WPACK_TC_DGRAD      3   /* [27 flipped][Cin][Cout]     */
 #define MEDNET_WPACK_TC_CONVT_F    4   /* transposed conv fprop: [8 parity classes][27 window taps][Cout][Cin] (8*27*Cin*Cout) */
 #define MEDNET_WPACK_TC_CONVT_B    5   /* transposed conv dgrad: [8 parity classes][27 window taps][Cin][Cout]                 */
+#define MEDNET_WPACK_TC_UPCONV_F   6   /* conv over a nearest-upsampled input, fprop: [8 output parity classes][27 coarse window taps]
+                                          [Cout][Cin], fine taps landing on the same coarse voxel summed (MEDNET_GATHER_UPCONV_F) */
+#define MEDNET_WPACK_TC_UPCONV_B   7   /* same, data gradient w.r.t. the coarse input: [8 dY parity classes][27][Cin][Cout]          */
 
 /* gather modes of the generic implicit GEMM */
 #define MEDNET_GATHER_CONV3   0   /* 3x3x3, stride 1, pad 1               */
 #define MEDNET_GATHER_CONVT_F 1   /* transposed k3 s2 p1 op1, output->input */
 #define MEDNET_GATHER_CONVT_B 2   /* transposed k3 s2 p1 op1, input->output */
+/* 3x3x3 conv (pad 1) of the NEAREST-UPSAMPLED (x2) input, computed on the coarse input itself -- the decoder join
+ * F.interpolate(x, 'nearest') + Conv3d of mm/unet/components.py:277-280 then :8-9.  For output voxel v = 2u + p the fine tap
+ * o in {-1,0,1} reads coarse voxel u + floor((p + o) / 2): 2 distinct coarse voxels per axis, so each of the 8 output parity
+ * classes is a 2x2x2 convolution over the coarse grid with summed weights (8 taps instead of 27; zero padding of the coarse
+ * grid == zero padding of the fine one).  UPCONV_F: x coarse [N,Di..] -> y fine [N,2Di..]; UPCONV_B: its data gradient, x = dY
+ * fine -> y = d(coarse input).  Tensor-core implementation only (bf16, sizes exactly x2). */
+#define MEDNET_GATHER_UPCONV_F 3
+#define MEDNET_GATHER_UPCONV_B 4
 
 /* error codes */
 #define MEDNET_OK            0
@@ -120,6 +131,11 @@ typedef struct {
   int32_t dtype, act; float act_param;
   int32_t gather;         /* MEDNET_GATHER_*                                                */
   int32_t impl;           /* MEDNET_IMPL_*                                                  */
+  /* fp32 partial sums between two launches that together form ONE convolution (tensor-core implementation only): the
+   * first launch writes y as fp32 without bias/addend/activation (y_f32 = 1), the second takes it as its addend
+   * (addend_f32 = 1) -- no rounding of the partial sum, so the pre-activation (and every ReLU' decision taken from it)
+   * is the one a single launch over all input channels would produce. */
+  int32_t y_f32, addend_f32;
 } mednet_conv3d_params;
 size_t mednet_conv3d_workspace_bytes(const mednet_conv3d_params* p);
 /* Resolves p->impl (MEDNET_IMPL_AUTO included) to the implementation that will run, so the caller can
@@ -282,6 +298,32 @@ typedef struct {
 size_t mednet_upcat_groupnorm_fwd_workspace_bytes(const mednet_upcat_gn_fwd_params* p);
 int    mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, void* workspace, size_t workspace_bytes,
                                   mednet_stream_t stream);
+/* Split variant for the upsample-aware decoder convolution (MEDNET_GATHER_UPCONV_*): same statistics over the virtual
+ * concat, but the normalised skip part is written at full resolution and the normalised low part on the COARSE grid (a
+ * per-channel affine commutes with nearest upsampling): the [N, D, H, W, Cs + Cl] tensor and its gradient never exist.
+ * Backward takes the gradients of the two outputs (dy_low already summed over the 8 children of each coarse voxel). */
+typedef struct {
+  const void*  skip; const void* low;
+  const float* gamma; const float* beta;
+  void*        y_skip;    /* [N, D, H, W, Cs] */
+  void*        y_low;     /* [N, d, h, w, Cl] */
+  float*       mean; float* rstd;
+  int32_t N, D, H, W, d, h, w, Cs, Cl, G, dtype; float eps;
+} mednet_upcat_gn_split_fwd_params;
+size_t mednet_upcat_groupnorm_split_fwd_workspace_bytes(const mednet_upcat_gn_split_fwd_params* p);
+int    mednet_upcat_groupnorm_split_fwd(const mednet_upcat_gn_split_fwd_params* p, void* workspace, size_t workspace_bytes,
+                                        mednet_stream_t stream);
+typedef struct {
+  const void*  skip; const void* low; const void* dy_skip; const void* dy_low;
+  const float* gamma; const float* mean; const float* rstd;
+  void*        dskip; void* dlow;
+  float*       dgamma; float* dbeta;
+  int32_t N, D, H, W, d, h, w, Cs, Cl, G, dtype, accumulate;
+  int32_t skip_act, low_act; float skip_act_param, low_act_param;
+} mednet_upcat_gn_split_bwd_params;
+size_t mednet_upcat_groupnorm_split_bwd_workspace_bytes(const mednet_upcat_gn_split_bwd_params* p);
+int    mednet_upcat_groupnorm_split_bwd(const mednet_upcat_gn_split_bwd_params* p, void* workspace, size_t workspace_bytes,
+                                        mednet_stream_t stream);
 typedef struct {
   const void*  skip; const void* low; const void* dy;      /* dy [N, D, H, W, Cs + Cl]           */
   const float* gamma; const float* mean; const float* rstd;

@@ -204,8 +204,12 @@ def layerwise_report(net, x, y, weight, f_maps):
                 _, j, skip, low, cat = join
                 s_, l_ = nd(skip).requires_grad_(), nd(low).requires_grad_()
                 gn = mod.groupnorm
-                xn = ops.UpcatGroupNormFn.apply(s_, l_, gn.weight, gn.bias, gn.num_groups, RELU, RELU)
-                yy = mod.run(xn, defer=True, skip_first=True)
+                if ops.upconv_supported(s_, l_, mod.conv.weight):      # the production branch of Decoder.run
+                    sn, ln = ops.UpcatGroupNormSplitFn.apply(s_, l_, gn.weight, gn.bias, gn.num_groups, RELU, RELU)
+                    yy = ops.UpConvJoinFn.apply(sn, ln, mod.conv.weight, RELU, True)
+                else:
+                    xn = ops.UpcatGroupNormFn.apply(s_, l_, gn.weight, gn.bias, gn.num_groups, RELU, RELU)
+                    yy = mod.run(xn, defer=True, skip_first=True)
                 add(prefix, "y", ncdhw(yy), yout)
                 yy.backward(dpre)
                 cs = skip.shape[1]

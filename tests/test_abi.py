@@ -26,7 +26,7 @@ def test_struct_layouts_follow_the_header(tmp_path):
     import subprocess
     s = _abi.STRUCTS["mednet_conv3d_params"]
     names = [f for f, _ in s._fields_]
-    assert names[:5] == ["x", "w", "bias", "addend", "y"] and names[-1] == "impl"
+    assert names[:5] == ["x", "w", "bias", "addend", "y"] and names[-3:] == ["impl", "y_f32", "addend_f32"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mednet_b200.h"', 'int main(void) {']
     for name, fields in _abi._STRUCT_FIELDS.items():
         lines.append(f'  printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {fields[-1][0]}));')

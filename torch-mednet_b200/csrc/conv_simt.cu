@@ -331,6 +331,49 @@ __global__ void pack_weights_convt_kernel(const float* __restrict__ src, T* __re
   }
 }
 
+// Packed weights of the conv over a nearest-upsampled input (MEDNET_GATHER_UPCONV_*): one [27][Nout][K] set per parity
+// class, indexed by COARSE window tap (offset + 1 per axis).  For v = 2u + p the fine tap o reads coarse voxel
+// u + c(p, o), c(0, .) = (-1, 0, 0), c(1, .) = (0, 0, +1) for o = (-1, 0, +1): the fine taps that land on the same coarse
+// voxel are summed.  src is the Conv3d weight (Cout, Cin, 3, 3, 3) of the upsampled input channels.
+//   fprop (dgrad = 0): window offset = c;   data gradient (dgrad = 1): dX[u] += W_p[c]^T dY[2 (u - c) + p]: offset = -c
+template <typename T>
+__global__ void pack_weights_upconv_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cin, int Cout, int dgrad) {
+  const int Nout = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
+  const int64_t total = (int64_t)8 * 27 * Nout * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int nout = (int)((i / K) % Nout);
+    const int tap = (int)((i / ((int64_t)K * Nout)) % 27);
+    const int cls = (int)(i / ((int64_t)K * Nout * 27));
+    const int kk[3] = {tap / 9, (tap / 3) % 3, tap % 3}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+    // per axis: the set of fine taps (as indices 0..2) that map to coarse offset c for this parity; empty = tap unused
+    int lo[3], hi[3];
+    bool on = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int c = dgrad ? 1 - kk[a] : kk[a] - 1;
+      if (par[a] == 0) {
+        if (c == -1) { lo[a] = 0; hi[a] = 0; }          // o = -1
+        else if (c == 0) { lo[a] = 1; hi[a] = 2; }       // o = 0, +1
+        else on = false;
+      } else {
+        if (c == 0) { lo[a] = 0; hi[a] = 1; }            // o = -1, 0
+        else if (c == 1) { lo[a] = 2; hi[a] = 2; }       // o = +1
+        else on = false;
+      }
+    }
+    float v = 0.f;
+    if (on) {
+      const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
+      const float* w = src + ((int64_t)co * Cin + ci) * 27;
+      for (int od = lo[0]; od <= hi[0]; ++od)
+        for (int oh = lo[1]; oh <= hi[1]; ++oh)
+          for (int ow = lo[2]; ow <= hi[2]; ++ow) v += w[(od * 3 + oh) * 3 + ow];
+    }
+    dst[i] = from_f32<T>(v);
+  }
+}
+
 int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int accumulate, void* workspace,
                 cudaStream_t st);
 
@@ -983,7 +1026,20 @@ using namespace mednet;
 extern "C" int mednet_conv3d_pack_weights(const mednet_wpack_params* p, mednet_stream_t stream) {
   MEDNET_REQUIRE(p && p->w_oidhw && p->w_packed && p->Cin > 0 && p->Cout > 0, MEDNET_EINVAL);
   MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
-  MEDNET_REQUIRE(p->layout >= 0 && p->layout <= 5, MEDNET_EINVAL);
+  MEDNET_REQUIRE(p->layout >= 0 && p->layout <= MEDNET_WPACK_TC_UPCONV_B, MEDNET_EINVAL);
+  if (p->layout == MEDNET_WPACK_TC_UPCONV_F || p->layout == MEDNET_WPACK_TC_UPCONV_B) {
+    MEDNET_REQUIRE(!p->transposed, MEDNET_EINVAL);
+    const int dg = p->layout == MEDNET_WPACK_TC_UPCONV_B ? 1 : 0;
+    const int64_t tot = (int64_t)8 * 27 * p->Cin * p->Cout;
+    if (p->dtype == MEDNET_F32)
+      pack_weights_upconv_kernel<float><<<grid_for(tot, 256), 256, 0, stream>>>((const float*)p->w_oidhw, (float*)p->w_packed,
+                                                                               p->Cin, p->Cout, dg);
+    else
+      pack_weights_upconv_kernel<bf16><<<grid_for(tot, 256), 256, 0, stream>>>((const float*)p->w_oidhw, (bf16*)p->w_packed,
+                                                                              p->Cin, p->Cout, dg);
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  }
   if (p->layout >= MEDNET_WPACK_TC_CONVT_F) {
     MEDNET_REQUIRE(p->transposed, MEDNET_EINVAL);
     const int dg = p->layout == MEDNET_WPACK_TC_CONVT_B ? 1 : 0;

@@ -84,6 +84,7 @@ struct TcConv {
   const float* bias;
   const bf16* addend;
   bf16* y;
+  int f32_io;                  // 0: bf16 output / addend; 1: y is fp32 (unrounded partial sum); 2: addend is fp32 (see mednet_conv3d_params)
 };
 
 struct TileCoord {
@@ -128,7 +129,9 @@ __device__ __forceinline__ float act_apply_t(float x, float a) {
 
 // Epilogue of one CTA (warps 3..6, one TMEM lane quadrant each): TMEM -> registers -> (+bias, +addend, activation) -> bf16
 // NDHWC rows.  Accumulator row m = voxel (h, w) of the brick plane.
-template <int ACT, bool PROF>
+// F32IO: 1 = the output is written as fp32 (a partial sum another launch completes: no rounding in between),
+//        2 = the addend is such an fp32 partial sum.
+template <int ACT, bool PROF, int F32IO = 0>
 __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
                                               int warp, int lane, long long* prof) {
   long long w_full = 0;
@@ -170,21 +173,36 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
               v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
             }
           }
-          if (arow != nullptr) {
+          if (F32IO == 2) {
+            const float4* aq = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + vox * p.Nout + tc_.n0 + j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 a4 = aq[i];
+              v[4 * i] += a4.x; v[4 * i + 1] += a4.y; v[4 * i + 2] += a4.z; v[4 * i + 3] += a4.w;
+            }
+          } else if (arow != nullptr) {
             float a0[8], a1[8];
             load_vec<bf16, 8>(arow + j, a0);
             load_vec<bf16, 8>(arow + j + 8, a1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[i] += a0[i]; v[8 + i] += a1[i]; }
           }
-          float o0[8], o1[8];
+          if (F32IO == 1) {
+            float4* yq = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + vox * p.Nout + tc_.n0 + j);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            o0[i] = act_apply_t<ACT>(v[i], p.act_param);
-            o1[i] = act_apply_t<ACT>(v[8 + i], p.act_param);
+            for (int i = 0; i < 4; ++i)
+              yq[i] = make_float4(act_apply_t<ACT>(v[4 * i], p.act_param), act_apply_t<ACT>(v[4 * i + 1], p.act_param),
+                                  act_apply_t<ACT>(v[4 * i + 2], p.act_param), act_apply_t<ACT>(v[4 * i + 3], p.act_param));
+          } else {
+            float o0[8], o1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o0[i] = act_apply_t<ACT>(v[i], p.act_param);
+              o1[i] = act_apply_t<ACT>(v[8 + i], p.act_param);
+            }
+            store_vec<bf16, 8>(yrow + j, o0);
+            store_vec<bf16, 8>(yrow + j + 8, o1);
           }
-          store_vec<bf16, 8>(yrow + j, o0);
-          store_vec<bf16, 8>(yrow + j + 8, o1);
         }
       }
     }
@@ -467,6 +485,14 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // the activation is a template parameter: a run-time switch inside the per-element code is compiled to either
     // selects or an indirect branch per element depending on unrelated details of the kernel (measured: 2x slower
     // epilogue-bound layers), so it is dispatched once per CTA here
+    if (p.f32_io == 1) {           // fp32 partial sum out: by contract without activation
+      epilogue_loop<MEDNET_ACT_NONE, PROF, 1>(p, tmem_base, acc_full, acc_empty, warp, lane, prof);
+    } else if (p.f32_io == 2) {    // fp32 partial sum in: the layers that use it end in ReLU or nothing
+      if (p.act == MEDNET_ACT_RELU) epilogue_loop<MEDNET_ACT_RELU, PROF, 2>(p, tmem_base, acc_full, acc_empty, warp, lane, prof);
+      else if (p.act == MEDNET_ACT_LEAKY) epilogue_loop<MEDNET_ACT_LEAKY, PROF, 2>(p, tmem_base, acc_full, acc_empty, warp, lane, prof);
+      else if (p.act == MEDNET_ACT_ELU) epilogue_loop<MEDNET_ACT_ELU, PROF, 2>(p, tmem_base, acc_full, acc_empty, warp, lane, prof);
+      else epilogue_loop<MEDNET_ACT_NONE, PROF, 2>(p, tmem_base, acc_full, acc_empty, warp, lane, prof);
+    } else
     switch (p.act) {
       case MEDNET_ACT_RELU: epilogue_loop<MEDNET_ACT_RELU, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
       case MEDNET_ACT_LEAKY: epilogue_loop<MEDNET_ACT_LEAKY, PROF>(p, tmem_base, acc_full, acc_empty, warp, lane, prof); break;
@@ -496,7 +522,11 @@ static int pick_row_bytes(int K) { return (K % 64 == 0) ? 128 : (K % 32 == 0) ? 
 static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   TcConv p;
   // the tile grid is the SMALLER of the two volumes for the transposed conv (its 8 parity classes tile the other one)
-  const bool tf = q->gather == MEDNET_GATHER_CONVT_F, tb = q->gather == MEDNET_GATHER_CONVT_B;
+  // "tf": 8 OUTPUT parity classes on the 2x grid (transposed conv fprop, upsample-conv fprop); "tb": 8 INPUT parity classes
+  // read through a stride-2 map (their data gradients); "up": the nearest-upsample conv (MEDNET_GATHER_UPCONV_*)
+  const bool up = q->gather == MEDNET_GATHER_UPCONV_F || q->gather == MEDNET_GATHER_UPCONV_B;
+  const bool tf = q->gather == MEDNET_GATHER_CONVT_F || q->gather == MEDNET_GATHER_UPCONV_F;
+  const bool tb = q->gather == MEDNET_GATHER_CONVT_B || q->gather == MEDNET_GATHER_UPCONV_B;
   p.N = q->N; p.K = q->K; p.Nout = q->Nout;
   p.D = tf ? q->Di : q->Do; p.H = tf ? q->Hi : q->Ho; p.W = tf ? q->Wi : q->Wo;
   p.OD = q->Do; p.OH = q->Ho; p.OW = q->Wo;
@@ -513,7 +543,9 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
       const int kk[3] = {tap / 9, (tap / 3) % 3, tap % 3}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
       bool on = true;
       for (int a = 0; a < 3; ++a) {
-        if (tf) on = on && (par[a] ? kk[a] >= 1 : kk[a] == 1);
+        if (up && tf) on = on && (par[a] ? kk[a] >= 1 : kk[a] <= 1);        // coarse offsets {0,+1} / {-1,0}
+        else if (up) on = on && (par[a] ? kk[a] <= 1 : kk[a] >= 1);         // gradient: mirrored
+        else if (tf) on = on && (par[a] ? kk[a] >= 1 : kk[a] == 1);
         else if (tb) on = on && (par[a] ? kk[a] <= 1 : kk[a] == 1);
       }
       if (on) m |= 1u << tap;
@@ -560,13 +592,15 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   if ((tf || tb) && p.per_row) return false;          // strided halo boxes are implemented for the dense halo only
   p.act = q->act; p.act_param = q->act_param;
   p.bias = q->bias; p.addend = (const bf16*)q->addend; p.y = (bf16*)q->y;
+  p.f32_io = q->y_f32 ? 1 : (q->addend_f32 && q->addend ? 2 : 0);
+  if (q->y_f32 && (q->act != MEDNET_ACT_NONE || q->addend != nullptr)) return false;
   *out = p;
   return true;
 }
 
 bool tc_fprop_supported(const mednet_conv3d_params* q) {
   if (q->dtype != MEDNET_BF16) return false;
-  if (q->gather != MEDNET_GATHER_CONV3 && q->gather != MEDNET_GATHER_CONVT_F && q->gather != MEDNET_GATHER_CONVT_B) return false;
+  if (q->gather < MEDNET_GATHER_CONV3 || q->gather > MEDNET_GATHER_UPCONV_B) return false;
   if (!mednet_device_has_tcgen05()) return false;
   if (((uintptr_t)q->x | (uintptr_t)q->w | (uintptr_t)q->y | (uintptr_t)q->addend | (uintptr_t)q->bias) & 15) return false;
   TcConv p;

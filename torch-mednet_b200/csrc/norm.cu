@@ -672,6 +672,84 @@ __global__ void upcat_gn_bwd_low_kernel(const T* __restrict__ low, const T* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm over the virtual concat, SPLIT outputs (decoder join feeding the upsample-aware convolution):
+// the normalised skip part stays at full resolution, the normalised low part stays on the COARSE grid
+// (a per-channel affine commutes with nearest upsampling).  Forward reuses gn_partial / upcat_gn_finalize / gn_apply
+// with per-part affine tables; backward reuses gn_bwd_partial / gn_bwd_apply with per-part coefficient tables.
+// ------------------------------------------------------------------------------------------------
+// ab[n][2][Cs + Cl] -> ab_a[n][2][Cs], ab_b[n][2][Cl]
+__global__ void split_ab_kernel(const float* __restrict__ ab, float* __restrict__ ab_a, float* __restrict__ ab_b, int N, int Cs,
+                                int Cl) {
+  const int C = Cs + Cl;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 2 * C) return;
+  const int c = i % C, w = (i / C) % 2, n = i / (2 * C);
+  if (c < Cs) ab_a[((int64_t)n * 2 + w) * Cs + c] = ab[i];
+  else ab_b[((int64_t)n * 2 + w) * Cl + c - Cs] = ab[i];
+}
+
+// one block per (n, g) of the virtual concat.  pa / pb: [n][nslab][2][Cs | Cl] sums of dy and dy*x over the skip part
+// (full resolution) and over the low part (coarse grid, dy already summed over the 8 children of each coarse voxel).
+//   skip:  dx = A dy + B x + Cc            low:  dx = A dy + 8 (B x + Cc)      (8 children share x)
+__global__ void split_gn_bwd_finalize_kernel(const float* __restrict__ pa, const float* __restrict__ pb,
+                                             const float* __restrict__ gamma, const float* __restrict__ mean,
+                                             const float* __restrict__ rstd, float* __restrict__ coef_a,
+                                             float* __restrict__ coef_b, float* __restrict__ dgb, int64_t S, int Cs, int Cl,
+                                             int G, int nslab_a, int nslab_b) {
+  __shared__ double scratch[32];
+  __shared__ double s_ds, s_db;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int C = Cs + Cl, cpg = C / G;
+  const double mu = (double)mean[n * G + g], rs = (double)rstd[n * G + g];
+  double ds = 0.0, db = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < cpg; i += nw) {
+    const int c = g * cpg + i;
+    const bool lo = c >= Cs;
+    const float* base = lo ? pb + (int64_t)n * nslab_b * 2 * Cl : pa + (int64_t)n * nslab_a * 2 * Cs;
+    const int Cp = lo ? Cl : Cs, cp = lo ? c - Cs : c, ns = lo ? nslab_b : nslab_a;
+    double s1 = 0.0, s2x = 0.0;
+    for (int slab = lane; slab < ns; slab += 32) {
+      s1 += (double)base[(int64_t)slab * 2 * Cp + cp];
+      s2x += (double)base[(int64_t)slab * 2 * Cp + Cp + cp];
+    }
+    s1 = warp_sum(s1);
+    s2x = warp_sum(s2x);
+    if (lane == 0) {
+      const double s2 = rs * (s2x - mu * s1);
+      dgb[((int64_t)n * 2 + 0) * C + c] = (float)s2;
+      dgb[((int64_t)n * 2 + 1) * C + c] = (float)s1;
+      ds += (double)gamma[c] * s2;
+      db += (double)gamma[c] * s1;
+    }
+  }
+  ds = block_sum(ds, scratch);
+  db = block_sum(db, scratch);
+  if (threadIdx.x == 0) {
+    s_ds = ds;
+    s_db = db;
+  }
+  __syncthreads();
+  const double m = (double)cpg * (double)S;
+  const double B = -rs * rs * s_ds / m;
+  const double Cc = rs * rs * s_ds * mu / m - rs * s_db / m;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
+    const int c = g * cpg + i;
+    const float A = (float)(rs * (double)gamma[c]);
+    if (c < Cs) {
+      coef_a[((int64_t)n * 3 + 0) * Cs + c] = A;
+      coef_a[((int64_t)n * 3 + 1) * Cs + c] = (float)B;
+      coef_a[((int64_t)n * 3 + 2) * Cs + c] = (float)Cc;
+    } else {
+      coef_b[((int64_t)n * 3 + 0) * Cl + c - Cs] = A;
+      coef_b[((int64_t)n * 3 + 1) * Cl + c - Cs] = (float)(8.0 * B);
+      coef_b[((int64_t)n * 3 + 2) * Cl + c - Cs] = (float)(8.0 * Cc);
+    }
+  }
+}
+
 }  // namespace mednet
 
 using namespace mednet;
@@ -921,6 +999,147 @@ extern "C" int mednet_upcat_groupnorm_bwd(const mednet_upcat_gn_bwd_params* p, v
       upcat_gn_bwd_low_kernel<T, VV><<<grid_for(total, 256), 256, 0, stream>>>((const T*)p->low, (const T*)p->dy, coef,
                                                                                (T*)p->dlow, p->N, p->D, p->H, p->W, p->Cs,
                                                                                p->Cl, p->low_act, p->low_act_param);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  return MEDNET_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- split variants
+namespace {
+struct SplitWs { size_t pa, pb, ab, ab_a, ab_b, total; };
+SplitWs split_fwd_ws(const UpcatPlan& u, int N, int Cs, int Cl) {
+  SplitWs w;
+  w.pa = 0;
+  w.pb = u.pa_bytes;
+  w.ab = w.pb + u.pb_bytes;
+  w.ab_a = w.ab + align_up((size_t)N * 2 * (Cs + Cl) * sizeof(float), 256);
+  w.ab_b = w.ab_a + align_up((size_t)N * 2 * Cs * sizeof(float), 256);
+  w.total = w.ab_b + align_up((size_t)N * 2 * Cl * sizeof(float), 256);
+  return w;
+}
+}  // namespace
+
+extern "C" size_t mednet_upcat_groupnorm_split_fwd_workspace_bytes(const mednet_upcat_gn_split_fwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || !upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G)) return 0;
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  return split_fwd_ws(u, p->N, p->Cs, p->Cl).total;
+}
+
+extern "C" int mednet_upcat_groupnorm_split_fwd(const mednet_upcat_gn_split_fwd_params* p, void* workspace,
+                                                size_t workspace_bytes, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->skip && p->low && p->gamma && p->beta && p->y_skip && p->y_low && p->mean && p->rstd, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_upcat_groupnorm_split_fwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  const SplitWs w = split_fwd_ws(u, p->N, p->Cs, p->Cl);
+  const int64_t S = (int64_t)p->D * p->H * p->W;
+  char* ws = (char*)workspace;
+  float* pa = (float*)(ws + w.pa);
+  float* pb = (float*)(ws + w.pb);
+  float* ab = (float*)(ws + w.ab);
+  float* ab_a = (float*)(ws + w.ab_a);
+  float* ab_b = (float*)(ws + w.ab_b);
+  for (int part = 0; part < 2; ++part) {
+    const SlabPlan& pl = part == 0 ? u.pa : u.pb;
+    const void* src = part == 0 ? p->skip : p->low;
+    const int Cp = part == 0 ? p->Cs : p->Cl;
+    const int64_t Sp = part == 0 ? S : S / 8;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)src, part == 0 ? pa : pb, Sp, Cp, pl.ncol,
+                                                              pl.rows_per_slab, pl.nslab);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  upcat_gn_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 2 * ((p->Cs + p->Cl) / p->G) * sizeof(double), stream>>>(
+      pa, pb, p->gamma, p->beta, p->mean, p->rstd, ab, S, p->Cs, p->Cl, p->G, u.pa.nslab, u.pb.nslab, p->eps);
+  MEDNET_LAUNCH_CHECK();
+  split_ab_kernel<<<ceil_div(p->N * 2 * (p->Cs + p->Cl), 256), 256, 0, stream>>>(ab, ab_a, ab_b, p->N, p->Cs, p->Cl);
+  MEDNET_LAUNCH_CHECK();
+  for (int part = 0; part < 2; ++part) {
+    const SlabPlan& pl = part == 0 ? u.pa : u.pb;
+    const int Cp = part == 0 ? p->Cs : p->Cl;
+    const int64_t Sp = part == 0 ? S : S / 8;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      gn_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)(part == 0 ? p->skip : p->low), (const T*)nullptr,
+                                                         (T*)(part == 0 ? p->y_skip : p->y_low), part == 0 ? ab_a : ab_b, Sp, Cp,
+                                                         pl.ncol, pl.rows_per_slab, MEDNET_ACT_NONE, 0.f);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  return MEDNET_OK;
+}
+
+namespace {
+struct SplitBwdWs { size_t pa, pb, coef_a, coef_b, dgb, total; };
+SplitBwdWs split_bwd_ws(const UpcatPlan& u, int N, int Cs, int Cl) {
+  SplitBwdWs w;
+  w.pa = 0;
+  w.pb = align_up((size_t)N * u.pa.nslab * 2 * Cs * sizeof(float), 256);
+  w.coef_a = w.pb + align_up((size_t)N * u.pb.nslab * 2 * Cl * sizeof(float), 256);
+  w.coef_b = w.coef_a + align_up((size_t)N * 3 * Cs * sizeof(float), 256);
+  w.dgb = w.coef_b + align_up((size_t)N * 3 * Cl * sizeof(float), 256);
+  w.total = w.dgb + align_up((size_t)N * 2 * (Cs + Cl) * sizeof(float), 256);
+  return w;
+}
+}  // namespace
+
+extern "C" size_t mednet_upcat_groupnorm_split_bwd_workspace_bytes(const mednet_upcat_gn_split_bwd_params* p) {
+  if (!p || !dtype_ok(p->dtype) || !upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G)) return 0;
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  return split_bwd_ws(u, p->N, p->Cs, p->Cl).total;
+}
+
+extern "C" int mednet_upcat_groupnorm_split_bwd(const mednet_upcat_gn_split_bwd_params* p, void* workspace,
+                                                size_t workspace_bytes, mednet_stream_t stream) {
+  MEDNET_REQUIRE(p && p->skip && p->low && p->dy_skip && p->dy_low && p->gamma && p->mean && p->rstd && p->dskip && p->dlow &&
+                     p->dgamma && p->dbeta, MEDNET_EINVAL);
+  MEDNET_REQUIRE(dtype_ok(p->dtype), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(upcat_geometry_ok(p->N, p->D, p->H, p->W, p->d, p->h, p->w, p->Cs, p->Cl, p->G), MEDNET_EUNSUPPORTED);
+  MEDNET_REQUIRE(workspace && workspace_bytes >= mednet_upcat_groupnorm_split_bwd_workspace_bytes(p), MEDNET_EWORKSPACE);
+  UpcatPlan u = upcat_plan(p->N, p->D, p->H, p->W, p->Cs, p->Cl, p->dtype);
+  const SplitBwdWs w = split_bwd_ws(u, p->N, p->Cs, p->Cl);
+  const int64_t S = (int64_t)p->D * p->H * p->W;
+  const int C = p->Cs + p->Cl;
+  char* ws = (char*)workspace;
+  float* pa = (float*)(ws + w.pa);
+  float* pb = (float*)(ws + w.pb);
+  float* coef_a = (float*)(ws + w.coef_a);
+  float* coef_b = (float*)(ws + w.coef_b);
+  float* dgb = (float*)(ws + w.dgb);
+  for (int part = 0; part < 2; ++part) {
+    const SlabPlan& pl = part == 0 ? u.pa : u.pb;
+    const int Cp = part == 0 ? p->Cs : p->Cl;
+    const int64_t Sp = part == 0 ? S : S / 8;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>(
+          (const T*)(part == 0 ? p->skip : p->low), (const T*)nullptr, (const T*)(part == 0 ? p->dy_skip : p->dy_low),
+          part == 0 ? pa : pb, Sp, Cp, pl.ncol, pl.rows_per_slab, pl.nslab, MEDNET_ACT_NONE, 0.f);
+    });
+    MEDNET_LAUNCH_CHECK();
+  }
+  split_gn_bwd_finalize_kernel<<<(unsigned)(p->N * p->G), 128, 0, stream>>>(pa, pb, p->gamma, p->mean, p->rstd, coef_a, coef_b,
+                                                                            dgb, S, p->Cs, p->Cl, p->G, u.pa.nslab, u.pb.nslab);
+  MEDNET_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(dgb, p->dgamma, p->dbeta, p->N, C, p->accumulate);
+  MEDNET_LAUNCH_CHECK();
+  for (int part = 0; part < 2; ++part) {
+    const SlabPlan& pl = part == 0 ? u.pa : u.pb;
+    const int Cp = part == 0 ? p->Cs : p->Cl;
+    const int64_t Sp = part == 0 ? S : S / 8;
+    dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      gn_bwd_apply_kernel<T, VV><<<grid, block, 0, stream>>>(
+          (const T*)(part == 0 ? p->skip : p->low), (const T*)nullptr, (const T*)(part == 0 ? p->dy_skip : p->dy_low),
+          part == 0 ? coef_a : coef_b, (T*)(part == 0 ? p->dskip : p->dlow), (T*)nullptr, Sp, Cp, pl.ncol, pl.rows_per_slab,
+          MEDNET_ACT_NONE, 0.f, part == 0 ? p->skip_act : p->low_act, part == 0 ? p->skip_act_param : p->low_act_param);
     });
     MEDNET_LAUNCH_CHECK();
   }

@@ -309,7 +309,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
 // dw[co][ci][kd][kh][kw] (+)= sum over splits of the partial accumulators, fixed order
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
-                                       int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset) {
+                                       int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset,
+                                       int upconv) {
   // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
   // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
@@ -318,7 +319,14 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     const int ci = (int)((i / 27) % Cin);
     const int co = (int)(i / (27 * (int64_t)Cin));
     int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    if (cls >= 0) {
+    if (cls >= 0 && upconv) {
+      // conv over the nearest-upsampled input: EVERY fine tap o receives a share from every dY parity class p, namely the
+      // class partial at window tap 1 - c(p, o) with c(0, .) = (-1, 0, 0), c(1, .) = (0, 0, +1)  (see MEDNET_GATHER_UPCONV_*)
+      const int pd = cls >> 2, ph = (cls >> 1) & 1, pw = cls & 1;
+      kd = pd ? (kd == 2 ? 0 : 1) : (kd == 0 ? 2 : 1);
+      kh = ph ? (kh == 2 ? 0 : 1) : (kh == 0 ? 2 : 1);
+      kw = pw ? (kw == 2 ? 0 : 1) : (kw == 0 ? 2 : 1);
+    } else if (cls >= 0) {
       // transposed conv: kernel tap k belongs to dY parity (k != 1) per axis and window tap (k == 0 ? 0 : 1)
       if ((((kd != 1) << 2) | ((kh != 1) << 1) | (kw != 1)) != cls) continue;
       kd = kd == 0 ? 0 : 1; kh = kh == 0 ? 0 : 1; kw = kw == 0 ? 0 : 1;
@@ -351,7 +359,7 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
       const float* src2 = src + (size_t)128 * PART_COLS - (size_t)gl * NCOLS;
       for (int k = 0; k < nk; ++k) acc += src2[(size_t)k * nw * 128 * PART_COLS];
     }
-    dw[i] = accumulate ? dw[i] + acc : acc;
+    dw[i] = (accumulate || (upconv && cls > 0)) ? dw[i] + acc : acc;      // upconv: classes 1..7 add to what class 0 wrote
   }
 }
 
@@ -366,7 +374,8 @@ struct WgPlan {
 
 bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   if (q->dtype != MEDNET_BF16) return false;
-  const bool convt = q->gather == MEDNET_GATHER_CONVT_B;      // a = x on the small grid, b = dY on the 2x grid
+  // a = x on the small grid, b = dY on the 2x grid (transposed conv, or the conv over a nearest-upsampled input)
+  const bool convt = q->gather == MEDNET_GATHER_CONVT_B || q->gather == MEDNET_GATHER_UPCONV_B;
   if (q->gather != MEDNET_GATHER_CONV3 && !convt) return false;
   if (convt && (q->Db != 2 * q->Da || q->Hb != 2 * q->Ha || q->Wb != 2 * q->Wa)) return false;
   if (!mednet_device_has_tcgen05()) return false;
@@ -457,7 +466,8 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   const void* u_ptr = pl.u_is_x ? q->b : q->a;
   const void* s_ptr = pl.u_is_x ? q->a : q->b;
   CUtensorMap map_u, map_s;
-  const bool convt = q->gather == MEDNET_GATHER_CONVT_B;
+  const bool upconv = q->gather == MEDNET_GATHER_UPCONV_B;
+  const bool convt = q->gather == MEDNET_GATHER_CONVT_B || upconv;
   {
     const cuuint64_t C = (cuuint64_t)a.CU;
     const cuuint64_t GD = pl.u_is_x ? q->Db : q->Da, GH = pl.u_is_x ? q->Hb : q->Ha, GW = pl.u_is_x ? q->Wb : q->Wa;
@@ -530,7 +540,8 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   auto reduce = [&](int cls) -> int {
     wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
         (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * 2,
-        q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats);
+        q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats,
+        upconv ? 1 : 0);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   };
@@ -544,9 +555,13 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     // (kd, kh) groups (mirrored when U is the strided operand); the reduce pass of each class writes only its taps
     for (int cls = 0; cls < 8; ++cls) {
       uint32_t gm = 0;
-      for (int kd = 0; kd < 2; ++kd)
-        for (int kh = 0; kh < 2; ++kh) {
-          if ((kd == 0 && !(cls & 4)) || (kh == 0 && !(cls & 2))) continue;     // window tap 0 exists for parity 1 only
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh) {
+          if (upconv) {    // dY parity 0: window taps {1, 2}, parity 1: {0, 1} (offset of the dY sub-grid = -c)
+            if (((cls & 4) ? kd > 1 : kd < 1) || ((cls & 2) ? kh > 1 : kh < 1)) continue;
+          } else {         // transposed conv: window tap 1 always, tap 0 for parity 1 only
+            if (kd == 2 || kh == 2 || (kd == 0 && !(cls & 4)) || (kh == 0 && !(cls & 2))) continue;
+          }
           const int gd = pl.u_is_x ? 2 - kd : kd, gh = pl.u_is_x ? 2 - kh : kh;
           gm |= 1u << (gd * 3 + gh);
         }

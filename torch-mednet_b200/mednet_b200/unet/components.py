@@ -336,8 +336,17 @@ class Decoder(nn.Module):
         if self.upsample is None:
             first = self.basic_module.SingleConv1 if isinstance(self.basic_module, DoubleConv) else None
             if first is not None and first.starts_with_plain_groupnorm and ops.upcat_gn_supported(encoder_features, x):
-                # GroupNorm over the virtual concat: the (N, Cs+Cl, S) concat tensor is never written
                 gn = first.groupnorm
+                dc = self.basic_module
+                if (len(first._plan) == 2 and first._plan[1][0] == 'c' and first.conv.bias is None and
+                        ops.upconv_supported(encoder_features, x, first.conv.weight)):
+                    # upsample-aware join: GroupNorm with split outputs, conv over skip + 8-tap conv over the COARSE low part
+                    sn, ln = ops.UpcatGroupNormSplitFn.apply(encoder_features, x, gn.weight, gn.bias, gn.num_groups,
+                                                             skip_act, x_act)
+                    inner = first.out_act if dc.SingleConv2.accepts_in_act else 0
+                    h = ops.UpConvJoinFn.apply(sn, ln, first.conv.weight, first._plan[1][1], bool(inner))
+                    return dc.SingleConv2.run(h, in_act=inner, defer=defer)
+                # GroupNorm over the virtual concat: the (N, Cs+Cl, S) concat tensor is never written
                 xn = ops.UpcatGroupNormFn.apply(encoder_features, x, gn.weight, gn.bias, gn.num_groups, skip_act, x_act)
                 return self.basic_module.run(xn, defer=defer, skip_first=True)
             x = ops.UpsampleConcatFn.apply(encoder_features, x, skip_act, x_act)
