@@ -156,7 +156,23 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
       const bf16* arow = p.addend ? p.addend + vox * p.Nout + tc_.n0 : nullptr;
       const uint32_t dcol = p.mt > 1 ? (uint32_t)(p.TD - 1 - dz) : (uint32_t)dz;     // kd-merged mode: decreasing d order
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.TD + dcol) * (uint32_t)p.Ntile;
-      for (int j = 0; j < p.Ntile; j += 16) {
+      for (int jb = 0; jb < p.Ntile; jb += 64) {
+      // fp32 partial-sum addend: all loads of a 64-channel block are issued before the first TMEM read (16 x 16 bytes in
+      // flight per thread; one load per use made the epilogue latency-bound and the MMA issuer wait for it)
+      float4 pre[4][4];
+      if (F32IO == 2 && inb) {
+        const float4* aq = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + vox * p.Nout + tc_.n0 + jb);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (jb + 16 * g < p.Ntile) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre[g][i] = aq[4 * g + i];
+          }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int j = jb + 16 * g;
+        if (j >= p.Ntile) break;
         uint32_t r[16];
         tc::tmem_ld_x16(taddr + (uint32_t)j, r);
         tc::tmem_ld_wait();
@@ -174,10 +190,9 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
             }
           }
           if (F32IO == 2) {
-            const float4* aq = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.addend) + vox * p.Nout + tc_.n0 + j);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 a4 = aq[i];
+              const float4 a4 = pre[g][i];
               v[4 * i] += a4.x; v[4 * i + 1] += a4.y; v[4 * i + 2] += a4.z; v[4 * i + 3] += a4.w;
             }
           } else if (arow != nullptr) {
@@ -204,6 +219,7 @@ __device__ __forceinline__ void epilogue_loop(const TcConv& p, uint32_t tmem_bas
             store_vec<bf16, 8>(yrow + j + 8, o1);
           }
         }
+      }
       }
     }
     if (p.mt > 1) tc::tmem_st_wait();

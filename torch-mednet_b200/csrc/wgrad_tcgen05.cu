@@ -55,6 +55,11 @@ struct WgArgs {
   // parity (cls >> 2, cls >> 1 & 1, cls & 1); one launch per parity class, only the (kd, kh) groups in gmask are needed
   int u_scale, s_scale, cls;
   uint32_t gmask;
+  // Balanced tap-group table (parity-class passes of the conv over an upsampled input: 4 of the 9 (kd, kh) groups are
+  // needed; with the fixed 0..4 / 4..8 role ranges one role would compute 3.5 of them and the other 0.5): slot s of role r
+  // holds group tab[r][s] (-1 = unused), no shared group.  use_tab = 0: the fixed ranges + gmask.
+  int use_tab;
+  signed char tab[2][5];
   int ut_base;                 // first U tile of this launch (the paired tail tile is launched separately)
   int pair_ok;                 // 1: U tiles with <= 64 real channels use the paired-plane mode (see kernel)
   int d_fastest;               // brick order inside a CTA: 1 = d fastest (halo planes reused from L2)
@@ -127,10 +132,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   // roles issue 4.5 MMAs per K step on average and the CTAs that read the same bricks stay in lockstep -- with a fixed
   // 5 / 4 split the faster role ran ahead and the shared bricks had to be fetched from HBM again (ncu: 2.5x the operand
   // bytes at 192x64@128^3).
-  const int ngroups = paired ? 3 : GROUPS0;
+  int tab_n = 0;
+  if (p.use_tab)
+    for (int i = 0; i < GROUPS0; ++i) tab_n += p.tab[role][i] >= 0 ? 1 : 0;
+  const int ngroups = p.use_tab ? tab_n : (paired ? 3 : GROUPS0);
   const int g0 = paired ? 0 : (role == 0 ? 0 : GROUPS0 - 1);
-  const int shared_slot = paired ? -1 : (role == 0 ? GROUPS0 - 1 : 0);
-  if (!paired && ((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u) return;   // this role owns no needed tap group (whole CTA)
+  const int shared_slot = (paired || p.use_tab) ? -1 : (role == 0 ? GROUPS0 - 1 : 0);
+  if (p.use_tab ? tab_n == 0 : (!paired && ((p.gmask >> g0) & ((1u << ngroups) - 1u)) == 0u))
+    return;                                                                  // this role owns no needed tap group (whole CTA)
   const int tiles_d = p.tiles_d + (paired ? 1 : 0);
   const int64_t bricks = (int64_t)p.N * tiles_d * p.tiles_h * p.tiles_w;
   const int64_t per_split = (bricks + p.ksplit - 1) / p.ksplit;
@@ -217,7 +226,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       uint32_t goff[GROUPS0];
 #pragma unroll
       for (int g = 0; g < GROUPS0; ++g) {
-        const int gg = g0 + (g < ngroups ? g : 0);
+        const int gg = p.use_tab ? (g < ngroups ? p.tab[role][g] : p.tab[role][0]) : g0 + (g < ngroups ? g : 0);
         const int gd = paired ? 1 + role : gg / 3, gh = paired ? gg : gg - gd * 3;
         goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W) * (2 * CS)) >> 4;
       }
@@ -238,7 +247,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
 #pragma unroll
       for (int g = 0; g < GROUPS0; ++g) {
         tmem_g[g] = tmem_base + (uint32_t)(g * NCOLS);
-        if (g < ngroups && (paired || ((p.gmask >> (g0 + g)) & 1u))) base_mask |= 1u << g;
+        if (g < ngroups && (paired || p.use_tab || ((p.gmask >> (g0 + g)) & 1u))) base_mask |= 1u << g;
       }
       const uint32_t shared_bit = shared_slot >= 0 ? (1u << shared_slot) : 0u;
       uint32_t it = 0;
@@ -256,6 +265,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         const bool shared_mine = (int)(b & 1) == role;          // which role computes the shared group for this brick
         if (paired) {
           wg_issue_brick<0, 3>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+        } else if (p.use_tab && ngroups == 2) {
+          wg_issue_brick<0, 2>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
         } else if (base_mask == 0x1fu) {
           if (shared_mine) wg_issue_brick<0, 5>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
           else if (role == 0) wg_issue_brick<0, 4>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
@@ -306,11 +317,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512u);
 }
 
+struct WgTab { int use; signed char where[9]; };     // where[group] = role * 8 + slot
+
 // dw[co][ci][kd][kh][kw] (+)= sum over splits of the partial accumulators, fixed order
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
                                        int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset,
-                                       int upconv) {
+                                       int upconv, WgTab tab) {
   // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
   // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
@@ -344,9 +357,14 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
       row = (cu & 63) + (kd == 0 ? 64 : 0);
     } else {
       const int g = kd * 3 + kh;               // role 0: groups 0..4 in slots 0..4; role 1: groups 4..8 in slots 0..4
-      role = g >= GROUPS0 ? 1 : 0;
-      gl = g - role * (GROUPS0 - 1);
-      shared = g == GROUPS0 - 1;               // group 4: role 0 slot 4 (even bricks) + role 1 slot 0 (odd bricks)
+      if (tab.use) {                           // balanced table: group g lives in (role, slot) = where[g]
+        role = tab.where[g] >> 3;
+        gl = tab.where[g] & 7;
+      } else {
+        role = g >= GROUPS0 ? 1 : 0;
+        gl = g - role * (GROUPS0 - 1);
+        shared = g == GROUPS0 - 1;             // group 4: role 0 slot 4 (even bricks) + role 1 slot 0 (odd bricks)
+      }
     }
     const int tile = cu >> 7;
     const bool s1 = tile >= seg1_tile;
@@ -391,7 +409,9 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   a.N = q->N; a.D = q->Da; a.H = q->Ha; a.W = q->Wa; a.CU = CU; a.CSn = CSn;
   a.u_scale = (convt && pl.u_is_x) ? 2 : 1;                   // "u_is_x": U is operand b
   a.s_scale = (convt && !pl.u_is_x) ? 2 : 1;
-  a.cls = 0; a.gmask = 0x1ffu;
+  a.cls = 0; a.gmask = 0x1ffu; a.use_tab = 0;
+  for (int r = 0; r < 2; ++r)
+    for (int i = 0; i < 5; ++i) a.tab[r][i] = -1;
   a.pair_ok = (!convt && g_pair_planes) ? 1 : 0;
   a.TD = q->Da >= 2 ? 2 : 1;
   a.tiles_d = ceil_div(a.D, a.TD); a.tiles_h = ceil_div(a.H, BR_H); a.tiles_w = ceil_div(a.W, BR_W);
@@ -537,11 +557,14 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     }
     return MEDNET_OK;
   };
+  WgTab wtab;
+  wtab.use = 0;
+  for (int i = 0; i < 9; ++i) wtab.where[i] = 0;
   auto reduce = [&](int cls) -> int {
     wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
         (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * 2,
         q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats,
-        upconv ? 1 : 0);
+        upconv ? 1 : 0, wtab);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   };
@@ -566,6 +589,19 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
           gm |= 1u << (gd * 3 + gh);
         }
       a.cls = cls; a.gmask = gm;
+      if (upconv) {      // the 4 needed groups, two per role
+        a.use_tab = 1; wtab.use = 1;
+        int cnt = 0;
+        for (int r = 0; r < 2; ++r)
+          for (int i = 0; i < 5; ++i) a.tab[r][i] = -1;
+        for (int g = 0; g < 9; ++g)
+          if ((gm >> g) & 1u) {
+            const int r = cnt / 2, sl = cnt % 2;
+            a.tab[r][sl] = (signed char)g;
+            wtab.where[g] = (signed char)(r * 8 + sl);
+            ++cnt;
+          }
+      }
       int r = launch_all();
       if (r != MEDNET_OK) return r;
       r = reduce(cls);

@@ -935,9 +935,10 @@ class UpConvJoinFn(torch.autograd.Function):
         sp = tuple(xs.shape[1:4])
         w = weight.detach()
         ws_, wl_ = w[:, :cs].contiguous(), w[:, cs:].contiguous()
-        # skip part: unrounded fp32 partial sum (a bf16 one would flip ~1e-3 of the ReLU' decisions: 3 % gradient noise)
-        y1 = k_conv3(xs, k_pack_weights(ws_, cs, cout, xs.dtype, 2), cout, sp, 0, 2, y_f32=True)
-        y = k_conv3(xl, k_pack_weights(wl_, cl, cout, xl.dtype, 6), cout, sp, 3, 2, addend=y1, act=act)
+        # coarse-grid part first, as an UNROUNDED fp32 partial sum (a bf16 one would move ~1e-3 of the pre-activations across
+        # zero: percent-level ReLU' noise); the full-resolution skip part adds it in its epilogue and applies the activation
+        y2 = k_conv3(xl, k_pack_weights(wl_, cl, cout, xl.dtype, 6), cout, sp, 3, 2, y_f32=True)
+        y = k_conv3(xs, k_pack_weights(ws_, cs, cout, xs.dtype, 2), cout, sp, 0, 2, addend=y2, act=act)
         bwd_act = 0 if defer_act else act
         ctx.save_for_backward(xs, xl, weight, y if bwd_act else None)
         ctx.act = bwd_act
