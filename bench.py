@@ -349,11 +349,16 @@ def conv_roofline(conv_events, ms_total, traffic, traffic_src):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else \
         "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
-    tc_flops = sum(f for f, _, _ in conv_events)
-    tc_ms = sum(a.elapsed_time(b) for _, a, b in conv_events)
+    tc_flops = sum(e[0] for e in conv_events)
+    ref_flops = sum(e[3] for e in conv_events)
+    tc_ms = sum(e[1].elapsed_time(e[2]) for e in conv_events)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     return {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM 3x3x3 fprop+dgrad)",
+            # achieved = FLOPs the launches EXECUTE / their time (tensor-pipe utilisation, <= 1 of peak).  The decoder
+            # join convolutions run 8 summed taps per voxel on the coarse grid instead of the reference op's 27
+            # (MEDNET_GATHER_UPCONV_*): reference_equivalent counts the reference op's FLOPs over the same time.
             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+            "reference_equivalent": ref_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_timed": len(conv_events),
             "share_of_step": tc_ms / ms_total if ms_total else None}
 

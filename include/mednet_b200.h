@@ -155,6 +155,11 @@ typedef struct {
   int32_t N, Da, Ha, Wa, Db, Hb, Wb, Ca, Cb;
   int32_t dtype, gather, impl;
   int32_t accumulate;     /* 1: dw += result (gradient accumulation), 0: overwrite                   */
+  /* Strided destination (tensor-core implementation): the (Ca,Cb,27) result is written into a weight-gradient tensor of
+   * `dw_ld` channels per row, starting at channel `dw_c0`: dw[(ca * dw_ld + dw_c0 + cb) * 27 + tap], or with
+   * dw_transposed dw[(cb * dw_ld + dw_c0 + ca) * 27 + tap].  dw_ld = 0: dense (Ca,Cb,3,3,3).  Lets the two halves of the
+   * decoder-join weight gradient (skip channels / upsampled channels) land in the one Conv3d gradient tensor. */
+  int32_t dw_ld, dw_c0, dw_transposed;
 } mednet_wgrad_params;
 size_t mednet_conv3d_wgrad_workspace_bytes(const mednet_wgrad_params* p);
 int    mednet_conv3d_wgrad_select_impl(const mednet_wgrad_params* p);

@@ -210,16 +210,22 @@ def test_async_weight_gradients_match_the_synchronous_path():
         opt.zero_grad()
         marked = sum(bool(getattr(p, "_mednet_async_grad", False)) for p in net.parameters())
         assert (marked > 0) == async_wgrad
-        for _ in range(2):                                   # accumulation over two backward passes
-            DiceLoss()(net(x), y).backward()
+        DiceLoss()(net(x), y).backward()
         opt.sync_gradients()
         torch.cuda.synchronize()
-        grads.append(opt.flat_grad.clone())
+        once = opt.flat_grad.clone()
+        DiceLoss()(net(x), y).backward()                     # accumulation over a second backward pass
+        opt.sync_gradients()
+        torch.cuda.synchronize()
+        grads.append((once, opt.flat_grad.clone()))
         opt.step()
         opt.zero_grad()
         assert float(opt.flat_grad.abs().sum()) == 0.0
-    assert torch.equal(grads[0], grads[1])
-    assert float(grads[0].abs().sum()) > 0
+    assert torch.equal(grads[0][0], grads[1][0])             # one pass: bit-identical
+    assert float(grads[0][0].abs().sum()) > 0
+    # accumulated: the decoder-join weight gradient is summed from 1 + 8 kernel passes; written straight into the
+    # accumulating buffer the fp32 additions associate differently than "sum the passes, then add" -- last-bit only
+    assert torch.allclose(grads[0][1], grads[1][1], rtol=1e-5, atol=1e-7 * float(grads[0][1].abs().max()))
 
 
 def test_resume_restores_optimizer_state_and_reproduces_the_uninterrupted_run(tmp_path):

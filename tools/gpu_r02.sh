@@ -55,14 +55,20 @@ if has launches; then
 fi
 if has kmetrics; then
   M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,launch__registers_per_thread,launch__grid_size
-  ncu --clock-control none --metrics $M -k regex:"${KREGEX:-^(conv|wgrad|gn_|upcat|maxpool|dice|adam|act_|pack_|cast_|transpose_|ce_|hm_|layout)}" -c ${KCOUNT:-300} --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
+  ncu --clock-control none --metrics $M -k regex:"${KREGEX:-^(conv|wgrad|gn_|upcat|maxpool|dice|adam|act_|pack_|cast_|transpose_|ce_|hm_|layout|border|affine|split)}" -c ${KCOUNT:-300} --csv --log-file $OUT/kernels_$TAG.csv $CMD > $OUT/ncu_d_$TAG.log 2>&1
   echo "ncu per-kernel metrics rc=$?"
   python tools/kernel_metrics.py $OUT/kernels_$TAG.csv > $OUT/kernels_$TAG.txt 2>&1; head -60 $OUT/kernels_$TAG.txt
 fi
 if has full; then
-  ncu --set full --clock-control none --import-source on -k regex:conv3_tc_kernel -s 20 -c 2 -f -o $OUT/conv3_tc_$TAG $CMD > $OUT/ncu_b_$TAG.log 2>&1
+  # the dominant kernel with the full set + source: launches 14..16 of a step = decoder-join coarse part (UPCONV_F), its
+  # full-resolution skip part (kd-merged, fp32 addend) and the kd-merged 64 -> 64 @ 128^3 layer
+  ncu --set full --clock-control none --import-source on -k regex:conv3_tc_kernel -s 13 -c 3 -f -o $OUT/conv3_tc_$TAG $CMD > $OUT/ncu_b_$TAG.log 2>&1
   echo "ncu conv full rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 10 -c 1 -f -o $OUT/wgrad_tc_$TAG $CMD > $OUT/ncu_c_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 0 -c 2 -f -o $OUT/wgrad_tc_$TAG $CMD > $OUT/ncu_c_$TAG.log 2>&1
   echo "ncu wgrad full rc=$?"
+  for K in conv3_tc wgrad_tc; do
+    ncu -i $OUT/${K}_$TAG.ncu-rep --page raw --csv > $OUT/${K}_${TAG}_raw.csv 2>/dev/null
+  done
+  ls -la $OUT/*.ncu-rep
 fi
 du -sh $OUT

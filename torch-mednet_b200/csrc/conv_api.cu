@@ -76,5 +76,6 @@ extern "C" int mednet_conv3d_wgrad(const mednet_wgrad_params* p, void* workspace
   const int impl = mednet_conv3d_wgrad_select_impl(p);
   if (impl < 0) return impl;
   if (impl == MEDNET_IMPL_TCGEN05) return tc_wgrad(p, workspace, stream);
+  MEDNET_REQUIRE(p->dw_ld == 0, MEDNET_EUNSUPPORTED);          // strided destinations: tensor-core implementation only
   return simt_wgrad(p, workspace, stream);
 }

@@ -323,7 +323,7 @@ struct WgTab { int use; signed char where[9]; };     // where[group] = role * 8 
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
                                        int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset,
-                                       int upconv, WgTab tab) {
+                                       int upconv, WgTab tab, int dw_ld, int dw_c0, int dw_transposed) {
   // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
   // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
@@ -377,7 +377,11 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
       const float* src2 = src + (size_t)128 * PART_COLS - (size_t)gl * NCOLS;
       for (int k = 0; k < nk; ++k) acc += src2[(size_t)k * nw * 128 * PART_COLS];
     }
-    dw[i] = (accumulate || (upconv && cls > 0)) ? dw[i] + acc : acc;      // upconv: classes 1..7 add to what class 0 wrote
+    // destination: dense (Ca, Cb, 27), or a channel range of a wider / transposed gradient tensor (mednet_wgrad_params)
+    const int64_t o = dw_ld == 0 ? i
+                                 : (dw_transposed ? ((int64_t)ci * dw_ld + dw_c0 + co) * 27 + tap
+                                                  : ((int64_t)co * dw_ld + dw_c0 + ci) * 27 + tap);
+    dw[o] = (accumulate || (upconv && cls > 0)) ? dw[o] + acc : acc;      // upconv: classes 1..7 add to what class 0 wrote
   }
 }
 
@@ -564,7 +568,7 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
         (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * 2,
         q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats,
-        upconv ? 1 : 0, wtab);
+        upconv ? 1 : 0, wtab, q->dw_ld, q->dw_c0, q->dw_transposed);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   };

@@ -18,7 +18,7 @@ IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
 
 launch_count = 0          # kernels-API calls issued (bench.py reads it for `gpu_launches`)
 wgrad_events = []         # same, per wgrad launch (tensor-core or SIMT, whichever ran)
-conv_events = None        # when a list: (algorithmic FLOPs, start event, end event) per tcgen05 conv launch
+conv_events = None        # when a list: (executed FLOPs, start event, end event, reference-op FLOPs) per tcgen05 conv launch
 
 
 def _dt(t):
@@ -216,16 +216,20 @@ def k_conv3(x, w_packed, nout, out_sp, gather, impl_id, bias=None, addend=None, 
     check(lib().mednet_conv3d_fprop(_abi.C.byref(p), _ptr(ws), ws.numel(), _stream()), "conv3d_fprop")
     if timing:
         e1.record()
-        conv_events.append((2.0 * n * out_sp[0] * out_sp[1] * out_sp[2] * k * nout * 27, e0, e1))
+        vo, vi = out_sp[0] * out_sp[1] * out_sp[2], di * hi * wi
+        # taps per output voxel: EXECUTED by the kernel / ALGORITHMIC (what the reference op performs: 27 per fine voxel)
+        taps, ref_taps = {0: (27, 27), 1: (27 / 8, 27 / 8), 2: (27, 27), 3: (8, 27), 4: (64, 216)}[gather]
+        conv_events.append((2.0 * n * vo * k * nout * taps, e0, e1, 2.0 * n * vo * k * nout * ref_taps))
     _count()
     return y
 
 
-def wgrad_params(a, b, gather, impl="auto", dw=None, dbias=None):
+def wgrad_params(a, b, gather, impl="auto", dw=None, dbias=None, ld=0, c0=0, transposed=False):
     n, da, ha, wa, ca = a.shape
     _, db, hb, wb, cb = b.shape
     return make("mednet_wgrad_params", a=_ptr(a), b=_ptr(b), dw=_ptr(dw), dbias=_ptr(dbias), N=n, Da=da, Ha=ha, Wa=wa,
-                Db=db, Hb=hb, Wb=wb, Ca=ca, Cb=cb, dtype=_dt(a), gather=gather, impl=IMPL[impl], accumulate=0)
+                Db=db, Hb=hb, Wb=wb, Ca=ca, Cb=cb, dtype=_dt(a), gather=gather, impl=IMPL[impl], accumulate=0,
+                dw_ld=ld, dw_c0=c0, dw_transposed=int(transposed))
 
 
 def k_wgrad(a, b, gather, impl="auto", want_bias=False):
@@ -294,10 +298,12 @@ def _async_wgrad_ok(weight):
             g.is_contiguous() and g.is_cuda)
 
 
-def k_wgrad_into(a, b, gather, impl, dw, accumulate=True):
-    """Weight gradient accumulated (or written) straight into `dw` (fp32, PyTorch layout) on the CURRENT stream."""
+def k_wgrad_into(a, b, gather, impl, dw, accumulate=True, ld=0, c0=0, transposed=False):
+    """Weight gradient accumulated (or written) straight into `dw` (fp32, PyTorch layout) on the CURRENT stream.
+    ld / c0 / transposed: `dw` is a wider gradient tensor of `ld` channels per row and the result goes to the channel range
+    starting at c0 (include/mednet_b200.h, mednet_wgrad_params)."""
     _need_cuda(a, b, dw)
-    p = wgrad_params(a, b, gather, impl, dw, None)
+    p = wgrad_params(a, b, gather, impl, dw, None, ld, c0, transposed)
     p.accumulate = int(accumulate)
     ws = _ws(lib().mednet_conv3d_wgrad_workspace_bytes(_abi.C.byref(p)), a.device)
     timing = conv_events is not None
@@ -940,6 +946,7 @@ class UpConvJoinFn(torch.autograd.Function):
         y2 = k_conv3(xl, k_pack_weights(wl_, cl, cout, xl.dtype, 6), cout, sp, 3, 2, y_f32=True)
         y = k_conv3(xs, k_pack_weights(ws_, cs, cout, xs.dtype, 2), cout, sp, 0, 2, addend=y2, act=act)
         bwd_act = 0 if defer_act else act
+        ctx.weight_ref = weight                      # the Parameter itself (its .grad buffer may be written asynchronously)
         ctx.save_for_backward(xs, xl, weight, y if bwd_act else None)
         ctx.act = bwd_act
         return y
@@ -958,9 +965,24 @@ class UpConvJoinFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dxl = k_conv3(dpre, k_pack_weights(wl_, cl, cout, dpre.dtype, 7), cl, tuple(xl.shape[1:4]), 4, 2)
         if ctx.needs_input_grad[2]:
-            dws, _ = k_wgrad(dpre, xs, 0, "auto")                        # (Cout, Cs, 3,3,3)
-            dwl, _ = k_wgrad(xl, dpre, 4, "tcgen05")                     # (Cl, Cout, 3,3,3): one pass per dY parity class
-            dw = torch.cat((dws, dwl.permute(1, 0, 2, 3, 4)), dim=1)     # data movement only
+            # both halves go straight into their channel range of the ONE (Cout, Cs + Cl, 3,3,3) gradient: the skip channels
+            # as (Cout, Cs), the upsampled channels from the per-parity-class passes, computed as (Cl, Cout), transposed
+            def both(dst, accumulate):
+                k_wgrad_into(dpre, xs, 0, "tcgen05", dst, accumulate, ld=cs + cl, c0=0)
+                k_wgrad_into(xl, dpre, 4, "tcgen05", dst, accumulate, ld=cs + cl, c0=cs, transposed=True)
+            if _async_wgrad_ok(ctx.weight_ref):
+                main, side = torch.cuda.current_stream(dpre.device), side_stream(dpre.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    both(ctx.weight_ref.grad, True)
+                for t in (dpre, xs, xl):
+                    t.record_stream(side)
+                _async_pending.add(dpre.device.index)
+                if async_grad_listener is not None:
+                    async_grad_listener(ctx.weight_ref)
+            else:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=weight.device)
+                both(dw, False)
         return dxs, dxl, dw, None, None
 
 
