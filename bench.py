@@ -447,6 +447,7 @@ def main():
     ap.add_argument("--conv-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     ap.add_argument("--kd-merge", type=int, default=1, help="tcgen05 conv: kd-merged wide-N MMAs (A/B switch)")
+    ap.add_argument("--wgrad-dual", type=int, default=1, help="tcgen05 wgrad: second MMA-issuing thread (A/B switch)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if wl.get("sampler"):
@@ -475,6 +476,7 @@ def main():
     from mednet_b200._abi import check, lib
     check(lib().mednet_tcgen05_set_option(b"dual_issue", args.dual_issue), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"kd_merge", args.kd_merge), "tcgen05_set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_dual_issue", args.wgrad_dual), "tcgen05_set_option")
     hp = hparams_for(wl)
     if wl["arch"] == "residual":
         cls = LandmarkNet if wl["heatmaps"] else SegmentationNet

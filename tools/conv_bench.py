@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--d-fastest", type=int, default=1)
     ap.add_argument("--kd-merge", type=int, default=1)
     ap.add_argument("--ntile-max", type=int, default=128)
+    ap.add_argument("--wgrad-dual", type=int, default=1)
     ap.add_argument("--layers", default="", help="comma-separated indices into LAYERS (default: all)")
     a = ap.parse_args()
     dev = "cuda"
@@ -56,6 +57,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"wgrad_d_fastest", a.d_fastest), "set_option")
     check(lib().mednet_tcgen05_set_option(b"kd_merge", a.kd_merge), "set_option")
     check(lib().mednet_tcgen05_set_option(b"ntile_max", a.ntile_max), "set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_dual_issue", a.wgrad_dual), "set_option")
     layers = [LAYERS[int(i)] for i in a.layers.split(",")] if a.layers else LAYERS
     for cin, cout, div in layers:
         s = a.edge // div

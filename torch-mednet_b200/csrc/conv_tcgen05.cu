@@ -773,6 +773,7 @@ extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_pair_planes") == 0) { tc_wgrad_set_pair_planes(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_d_fastest") == 0) { tc_wgrad_set_d_fastest(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_profile") == 0) { tc_wgrad_set_profile(value); return MEDNET_OK; }
+  if (strcmp(name, "wgrad_dual_issue") == 0) { tc_wgrad_set_dual(value); return MEDNET_OK; }
   return MEDNET_EINVAL;
 }
 

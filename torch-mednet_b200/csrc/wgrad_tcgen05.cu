@@ -33,9 +33,10 @@ namespace {
 int g_pair_planes = 1;        // mednet_tcgen05_set_option("wgrad_pair_planes", 0|1)
 int g_d_fastest = 1;          // mednet_tcgen05_set_option("wgrad_d_fastest", 0|1)
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
+int g_dual = 1;               // mednet_tcgen05_set_option("wgrad_dual_issue", 0|1)
 int g_profile = 0;            // mednet_tcgen05_set_option("wgrad_profile", 0|1): wait-cycle counters, see wgrad_tc_kernel<PROF>
 
-constexpr int WG_THREADS = 192;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue
+constexpr int WG_THREADS = 224;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue, warp 6: second MMA issuer
 constexpr int BR_H = 16, BR_W = 8;       // brick (h, w); depth TD
 constexpr int HL_H = 18, HL_W = 10;      // halo plane
 constexpr int CS = 32;                   // S channels per CTA (64-byte rows, SWIZZLE_64B)
@@ -60,6 +61,10 @@ struct WgArgs {
   // holds group tab[r][s] (-1 = unused), no shared group.  use_tab = 0: the fixed ranges + gmask.
   int use_tab;
   signed char tab[2][5];
+  // second MMA-issuing thread (warp 6).  One thread sustains one tcgen05.mma per ~55-64 clk, the N = 96 MMA needs 56 clk of
+  // shared-memory operand reads: two issuers, each owning a disjoint range of the CTA's tap-group accumulators, move the
+  // bound from the issue rate to the operand rate (same scheme as the conv kernel's dual issue).
+  int dual;
   int ut_base;                 // first U tile of this launch (the paired tail tile is launched separately)
   int pair_ok;                 // 1: U tiles with <= 64 real channels use the paired-plane mode (see kernel)
   int d_fastest;               // brick order inside a CTA: 1 = d fastest (halo planes reused from L2)
@@ -148,8 +153,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   if (b_end > bricks) b_end = bricks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(done, 1);
+    const uint32_t nissue = p.dual ? 2u : 1u;        // every issuer commits to the barriers its MMAs release
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], nissue); }
+    tc::mbar_init(done, nissue);
     tc::fence_barrier_init();
     tc::tma_prefetch_desc(&map_u);
     tc::tma_prefetch_desc(&map_s);
@@ -166,7 +172,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   {
     // every accumulator slot starts at zero, so every MMA accumulates: no first-MMA special case in the issue loop, and the
     // shared slot (which this CTA's first brick may not touch) needs no separate treatment
-    if (warp >= 2) {
+    if (warp >= 2 && warp <= 5) {
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       for (int j = 0; j < ngroups * NCOLS; j += 16) tc::tmem_st_x16_zero(taddr + (uint32_t)j);
       tc::tmem_st_wait();
@@ -218,9 +224,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       }
       if (PROF) prof[2] = w_empty;
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (tc::elect_one()) {
+  } else if (warp == 1 || warp == 6) {
+    // ===================== MMA issuer(s) =====================
+    const int issuer = warp == 1 ? 0 : 1;
+    if ((issuer == 0 || p.dual) && tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_16(128, NCOLS, 1, 1, 1, 1);
       // per-group window offset inside the halo, in descriptor units (16 bytes)
       uint32_t goff[GROUPS0];
@@ -263,14 +270,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         // bit mask evaluated per brick, not per MMA.
         const uint32_t a_st = a_lo0 + st * stage16, b_st = b_lo0 + st * stage16;
         const bool shared_mine = (int)(b & 1) == role;          // which role computes the shared group for this brick
-        if (paired) {
-          wg_issue_brick<0, 3>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+#define WG_BRICK(GB, GE) wg_issue_brick<GB, GE>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16)
+        if (p.dual) {
+          // each issuer owns a disjoint range of the brick's tap groups (their accumulators are disjoint TMEM columns)
+          if (paired) { if (issuer == 0) WG_BRICK(0, 2); else WG_BRICK(2, 3); }
+          else if (p.use_tab && ngroups == 2) { if (issuer == 0) WG_BRICK(0, 1); else WG_BRICK(1, 2); }
+          else if (base_mask == 0x1fu) {
+            if (shared_mine) { if (issuer == 0) WG_BRICK(0, 3); else WG_BRICK(3, 5); }
+            else if (role == 0) { if (issuer == 0) WG_BRICK(0, 2); else WG_BRICK(2, 4); }
+            else { if (issuer == 0) WG_BRICK(1, 3); else WG_BRICK(3, 5); }
+          } else {
+            const uint32_t act = (shared_mine ? base_mask : (base_mask & ~shared_bit)) & (issuer == 0 ? 0x15u : 0x0au);
+            for (int dz = 0; dz < p.TD; ++dz) {
+              uint32_t a_lo = a_st + (uint32_t)dz * a_dz16, b_lo = b_st + (uint32_t)dz * b_dz16;
+              for (int hp = 0; hp < 8; ++hp) {
+#pragma unroll
+                for (int g = 0; g < GROUPS0; ++g)
+                  if ((act >> g) & 1u) tc::umma_bf16_lohi(tmem_g[g], a_lo, a_hi, b_lo + goff[g], b_hi, idesc, 1u);
+                a_lo += a_hp16;
+                b_lo += b_hp16;
+              }
+            }
+          }
+        } else if (paired) {
+          WG_BRICK(0, 3);
         } else if (p.use_tab && ngroups == 2) {
-          wg_issue_brick<0, 2>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+          WG_BRICK(0, 2);
         } else if (base_mask == 0x1fu) {
-          if (shared_mine) wg_issue_brick<0, 5>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
-          else if (role == 0) wg_issue_brick<0, 4>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
-          else wg_issue_brick<1, 5>(p.TD, a_st, b_st, a_hi, b_hi, idesc, tmem_g, goff, a_dz16, b_dz16, a_hp16, b_hp16);
+          if (shared_mine) WG_BRICK(0, 5);
+          else if (role == 0) WG_BRICK(0, 4);
+          else WG_BRICK(1, 5);
         } else {
           // transposed-conv parity classes: only the tap groups of gmask (at most 4 of 9), rare and small launches
           const uint32_t act = shared_mine ? base_mask : (base_mask & ~shared_bit);
@@ -288,7 +317,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         tc::umma_commit(&empty[st]);
       }
       tc::umma_commit(done);
-      if (PROF) { tc::mbar_wait(done, 0); prof[0] = clock64() - t_begin; prof[1] = w_full; prof[3] = b_end - b_begin; }
+#undef WG_BRICK
+      if (PROF && issuer == 0) { tc::mbar_wait(done, 0); prof[0] = clock64() - t_begin; prof[1] = w_full; prof[3] = b_end - b_begin; }
     }
   } else {
     // ===================== epilogue (once per CTA) =====================
@@ -413,7 +443,7 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   a.N = q->N; a.D = q->Da; a.H = q->Ha; a.W = q->Wa; a.CU = CU; a.CSn = CSn;
   a.u_scale = (convt && pl.u_is_x) ? 2 : 1;                   // "u_is_x": U is operand b
   a.s_scale = (convt && !pl.u_is_x) ? 2 : 1;
-  a.cls = 0; a.gmask = 0x1ffu; a.use_tab = 0;
+  a.cls = 0; a.gmask = 0x1ffu; a.use_tab = 0; a.dual = g_dual;
   for (int r = 0; r < 2; ++r)
     for (int i = 0; i < 5; ++i) a.tab[r][i] = -1;
   a.pair_ok = (!convt && g_pair_planes) ? 1 : 0;
@@ -462,6 +492,7 @@ void tc_wgrad_set_wt_fastest(int v) { g_wt_fastest = v ? 1 : 0; }
 void tc_wgrad_set_pair_planes(int v) { g_pair_planes = v ? 1 : 0; }
 void tc_wgrad_set_d_fastest(int v) { g_d_fastest = v ? 1 : 0; }
 void tc_wgrad_set_profile(int v) { g_profile = v ? 1 : 0; }
+void tc_wgrad_set_dual(int v) { g_dual = v ? 1 : 0; }
 size_t tc_wgrad_profile_offset(const mednet_wgrad_params* q) {
   WgPlan pl;
   if (!plan_wgrad(q, &pl)) return 0;
