@@ -19,7 +19,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OUT_DIR = os.path.join(os.path.dirname(HERE), "mednet_b200")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "libmednet_b200.so")
-SOURCES = ["norm.cu", "glue.cu", "conv_simt.cu", "conv1x1.cu", "loss.cu", "misc.cu", "augment.cu", "input_affine.cu", "conv_api.cu", "conv_tcgen05.cu",
+SOURCES = ["norm.cu", "glue.cu", "conv_simt.cu", "conv1x1.cu", "loss.cu", "misc.cu", "augment.cu", "input_affine.cu", "first_layer_mma.cu", "conv_api.cu", "conv_tcgen05.cu",
            "wgrad_tcgen05.cu", "umma_lab.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

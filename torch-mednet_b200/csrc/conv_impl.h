@@ -13,6 +13,13 @@ size_t colsum_workspace_bytes(const mednet_wgrad_params* p);
 int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int accumulate, void* workspace,
                 cudaStream_t st);
 
+// first layer (in_channels = 1) on warp-level mma.sync (first_layer_mma.cu)
+void in1_mma_set_enabled(int v);
+bool in1_mma_fprop_ok(const mednet_conv3d_params* p);
+int in1_mma_fprop(const mednet_conv3d_params* p, cudaStream_t st);
+bool in1_mma_wgrad_ok(const mednet_wgrad_params* p);
+int in1_mma_wgrad(const mednet_wgrad_params* p, float* partial, int max_blocks, int* blocks_out, cudaStream_t st);
+
 bool tc_fprop_supported(const mednet_conv3d_params* p);
 int tc_fprop(const mednet_conv3d_params* p, void* workspace, size_t workspace_bytes, cudaStream_t st);
 bool tc_wgrad_supported(const mednet_wgrad_params* p);

@@ -6,6 +6,7 @@
 //   * both weight gradients (deterministic split-K)
 // through a `gather` rule mapping (row voxel, tap) -> source voxel.
 #include "common.cuh"
+#include "conv_impl.h"
 
 namespace mednet {
 
@@ -881,6 +882,18 @@ static int fewin_wgrad_t(const mednet_wgrad_params* p, void* workspace, cudaStre
   float* partial = (float*)workspace;
   const size_t pbytes = align_up((size_t)blocks * p->Ca * 27 * p->Cb * sizeof(float), 256);
   const size_t smem = ((size_t)WSEG * p->Ca + 9 * (WSEG + 2) * p->Cb) * sizeof(float);
+  if (in1_mma_wgrad_ok(p)) {                                  // bf16, one gathered channel: warp-level tensor cores
+    int nb = blocks;
+    const int r = in1_mma_wgrad(p, partial, blocks, &nb, st);
+    if (r != MEDNET_OK) return r;
+    const int64_t tot = (int64_t)p->Ca * 27;
+    wgrad_reduce_kernel<<<grid_for(tot, 256), 256, 0, st>>>(partial, p->dw, p->Ca, p->Cb, nb, p->accumulate);
+    MEDNET_LAUNCH_CHECK();
+    if (p->dbias != nullptr)
+      return colsum_bias(p->a, p->dtype, (int64_t)p->N * p->Da * p->Ha * p->Wa, p->Ca, p->dbias, p->accumulate,
+                         (char*)workspace + pbytes, st);
+    return MEDNET_OK;
+  }
   if (p->Cb == 1 && p->Ca >= 16) {
     // chunk of WSEG / (256 / Ca) = Ca / 4 voxels per thread = PIECES quads
     size_t sm1 = ((size_t)p->Ca * DYS_PITCH + 9 * XS_PITCH) * sizeof(float);
@@ -956,6 +969,7 @@ int colsum_bias(const void* a, int dtype, int64_t M, int C, float* dbias, int ac
 
 template <typename T>
 static int small_fprop_t(const mednet_conv3d_params* p, cudaStream_t st) {
+  if (in1_mma_fprop_ok(p)) return in1_mma_fprop(p, st);      // bf16, one input channel: warp-level tensor cores
   const int HW = p->Ho * p->Wo;
   if (fewin_fprop_ok(p) && p->Nout % 16 == 0 && p->Wo >= 4) {
     dim3 grid(ceil_div(p->Ho * ceil_div(p->Wo, 4), 128), (unsigned)(p->N * p->Do), p->Nout / 16);

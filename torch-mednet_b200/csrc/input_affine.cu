@@ -28,23 +28,32 @@ __global__ void border_class_partial_kernel(const T* __restrict__ x, float* __re
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[b][c][i] = 0.f;
+  // UR rows per iteration: all their 16-byte loads are issued before the first add (memory-level parallelism)
+  constexpr int UR = 4;
   auto rows = [&](int h0, int h1, float (&a)[3][V]) {
-    for (int h = h0; h < h1; ++h) {
-      const T* row = plane + (int64_t)h * W * C;
-#pragma unroll 2
+    for (int h = h0; h < h1; h += UR) {
       for (int w = ty; w < W; w += R) {
-        float v[V];
-        load_vec<T, V>(row + (int64_t)w * C, v);
-        if (w == 0) {
+        typename RawVec<sizeof(T) * V>::type raw[UR];
 #pragma unroll
-          for (int i = 0; i < V; ++i) a[1][i] += v[i];
-        } else if (w == W - 1) {
+        for (int u = 0; u < UR; ++u)
+          if (h + u < h1) raw[u] = load_raw<T, V>(plane + ((int64_t)(h + u) * W + w) * C);
+        const int cls = w == 0 ? 1 : (w == W - 1 ? 2 : 0);
 #pragma unroll
-          for (int i = 0; i < V; ++i) a[2][i] += v[i];
-        } else {
+        for (int u = 0; u < UR; ++u)
+          if (h + u < h1) {
+            float v[V];
+            cvt_raw<T, V>(raw[u], v);
+            if (cls == 0) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) a[0][i] += v[i];
-        }
+              for (int i = 0; i < V; ++i) a[0][i] += v[i];
+            } else if (cls == 1) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) a[1][i] += v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < V; ++i) a[2][i] += v[i];
+            }
+          }
       }
     }
   };
