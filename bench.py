@@ -219,32 +219,85 @@ def run_reference_arm(args, wl):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (every 100 ms).  NVML is queried from a thread of this
+    process: `prepare()` (NVML init, device handle) runs before the warm-up, so nothing is started inside the timed region
+    -- spawning `nvidia-smi -lms` there was measured to stretch a 0.4 s region by up to 27 % while the tool initialised.
+    Falls back to an `nvidia-smi` loop started in prepare() (i.e. before the warm-up) when pynvml is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.proc, self.index = None, index
+        self.index, self.nvml, self.handle, self.proc = index, None, None, None
+        self.samples, self.thread, self.running = [], None, False
+        self.smi_skip = 0
+
+    def prepare(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if len(ids) > self.index else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
+
+    def _loop(self):
+        n = self.nvml
+        while self.running:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        if self.nvml is not None:
+            import threading
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        else:
+            self.t_start = time.time()
 
     def stop(self):
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            n = self.nvml
+            names = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            sm = [m for m, _ in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(b & bit for _, b in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "NVML, 100 ms, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        dur = time.time() - self.t_start
         self.proc.terminate()
         try:
             out = self.proc.communicate(timeout=5)[0]
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out = ""
+        lines = out.strip().splitlines()
+        lines = lines[-max(1, int(dur / 0.2) + 1):]              # the samples of the timed region (200 ms apart)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
@@ -257,7 +310,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200 started before the warm-up"}
 
 
 # ------------------------------------------------------------------------------------------------ predict arm
@@ -299,9 +352,11 @@ def run_predict(args, wl):
 
     from mednet_b200 import ops
     steps, warm = max(1, min(args.steps, 3)), 1
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
     for _ in range(warm):
         pred(vol_dev)
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ops.conv_events = []
@@ -517,6 +572,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
     t_warm = time.perf_counter()
     for _ in range(args.warmup):
         step(batch_dev)
@@ -528,7 +586,6 @@ def main():
         step(batch_dev)
         torch.cuda.synchronize()
     step({k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}).item()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ops.conv_events = []                     # per-launch CUDA events of the dominant kernel (see ops.k_conv3)

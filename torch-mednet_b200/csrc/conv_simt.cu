@@ -323,11 +323,9 @@ __global__ void pack_weights_convt_kernel(const float* __restrict__ src, T* __re
       else if (!dgrad) { on = on && off >= 0; ksrc[a] = off == 0 ? 2 : 0; }
       else { on = on && off <= 0; ksrc[a] = off == 0 ? 2 : 0; }
     }
-    float v = 0.f;
-    if (on) {
-      const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
-      v = src[((int64_t)ci * Cout + co) * 27 + (ksrc[0] * 3 + ksrc[1]) * 3 + ksrc[2]];
-    }
+    if (!on) continue;           // inactive taps of a parity class are never loaded by the kernel (tap mask): not written
+    const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
+    const float v = src[((int64_t)ci * Cout + co) * 27 + (ksrc[0] * 3 + ksrc[1]) * 3 + ksrc[2]];
     dst[i] = from_f32<T>(v);
   }
 }
@@ -363,8 +361,9 @@ __global__ void pack_weights_upconv_kernel(const float* __restrict__ src, T* __r
         else on = false;
       }
     }
+    if (!on) continue;           // taps outside the class's 2x2x2 window are never loaded by the kernel (tap mask): not written
     float v = 0.f;
-    if (on) {
+    {
       const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
       const float* w = src + ((int64_t)co * Cin + ci) * 27;
       for (int od = lo[0]; od <= hi[0]; ++od)
