@@ -582,18 +582,27 @@ def main():
     # (a 3-step warm-up was measured 7 % slower in the first timed region than in the one after it); keep stepping,
     # untimed, until the warm-up has lasted ~1.5 s, and run the host-batch path once as well
     torch.cuda.synchronize()
-    while time.perf_counter() - t_warm < 1.5:
+    recent, best = [], float("inf")
+    while True:
+        t0 = time.perf_counter()
         step(batch_dev)
         torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        recent = (recent + [dt])[-3:]
+        elapsed = time.perf_counter() - t_warm
+        # settled: >= 1.5 s of warm-up and the last three steps within 2 % of the fastest seen (or 8 s, whatever comes first)
+        if elapsed > 8.0 or (elapsed > 1.5 and len(recent) == 3 and max(recent) < 1.02 * best):
+            break
     step({k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}).item()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("MEDNET_BENCH_NOSAMPLER"):
         sampler.start()
-    ops.conv_events = []                     # per-launch CUDA events of the dominant kernel (see ops.k_conv3)
+    ops.conv_events = None if os.environ.get("MEDNET_BENCH_NOEVENTS") else []   # per-launch CUDA events (see ops.k_conv3)
     launches0 = ops.launch_count
     ms = timed(lambda: step(batch_dev), args.steps)
     launches = ops.launch_count - launches0
-    conv_events, ops.conv_events = ops.conv_events, None
-    clocks = sampler.stop() if rank == 0 else None
+    conv_events, ops.conv_events = ops.conv_events or [], None
+    clocks = sampler.stop() if (rank == 0 and sampler.running) else None
 
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}

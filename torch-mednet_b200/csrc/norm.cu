@@ -50,17 +50,26 @@ static SlabPlan make_plan(int64_t N, int64_t S, int C, int elem_bytes, int force
 }
 
 // reduce NV per-thread floats across threadIdx.y; the result for value i lands in the thread with
-// (i % R == ty) which calls emit(i, total).
+// (i % RED_CHUNK % R == ty) which calls emit(i, total).  Done in chunks of RED_CHUNK values so that the scratch is
+// blockDim * RED_CHUNK floats (4 KB for 256 threads) whatever NV is: the statistics kernels then fit beside a resident
+// tensor-core CTA (224 KB of the SM's 228 KB) and can run UNDER the asynchronous weight gradients instead of waiting for
+// an SM to drain.  Fixed summation order: deterministic.
+constexpr int RED_CHUNK = 4;
 template <int NV, typename Emit>
 __device__ __forceinline__ void reduce_over_y(const float (&vals)[NV], float* sm, Emit emit) {
   const int bx = blockDim.x, R = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) sm[(ty * bx + tx) * NV + i] = vals[i];
-  __syncthreads();
-  for (int i = ty; i < NV; i += R) {
-    float acc = 0.f;
-    for (int t = 0; t < R; ++t) acc += sm[(t * bx + tx) * NV + i];
-    emit(i, acc);
+  for (int c0 = 0; c0 < NV; c0 += RED_CHUNK) {
+    if (c0 > 0) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RED_CHUNK; ++j)
+      if (c0 + j < NV) sm[(ty * bx + tx) * RED_CHUNK + j] = vals[c0 + j];
+    __syncthreads();
+    for (int j = ty; j < RED_CHUNK && c0 + j < NV; j += R) {
+      float acc = 0.f;
+      for (int t = 0; t < R; ++t) acc += sm[(t * bx + tx) * RED_CHUNK + j];
+      emit(c0 + j, acc);
+    }
   }
 }
 
@@ -773,7 +782,7 @@ extern "C" int mednet_groupnorm_fwd(const mednet_gn_fwd_params* p, void* workspa
   float* ab = (float*)((char*)workspace + align_up((size_t)p->N * (pl.nslab + 1) * 2 * p->C * sizeof(float), 256));
   dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
   MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-    size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+    size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
     gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->x, partial, p->S, p->C, pl.ncol,
                                                             pl.rows_per_slab, pl.nslab);
   });
@@ -814,7 +823,7 @@ extern "C" int mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspa
   float* dgb = (float*)ws;
   dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
   MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-    size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+    size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
     gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy,
                                                                 partial, p->S, p->C, pl.ncol, pl.rows_per_slab,
                                                                 pl.nslab, p->act, p->act_param);
@@ -911,7 +920,7 @@ extern "C" int mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, v
     const SlabPlan& pl = u.pa;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
       gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->skip, pa, S, p->Cs, pl.ncol, pl.rows_per_slab,
                                                               pl.nslab);
     });
@@ -921,7 +930,7 @@ extern "C" int mednet_upcat_groupnorm_fwd(const mednet_upcat_gn_fwd_params* p, v
     const SlabPlan& pl = u.pb;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
       gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->low, pb, S / 8, p->Cl, pl.ncol, pl.rows_per_slab,
                                                               pl.nslab);
     });
@@ -971,7 +980,7 @@ extern "C" int mednet_upcat_groupnorm_bwd(const mednet_upcat_gn_bwd_params* p, v
     const SlabPlan& pl = u.pc;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
       upcat_gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)p->skip, (const T*)p->low, (const T*)p->dy,
                                                                         partial, p->D, p->H, p->W, p->Cs, p->Cl, pl.ncol,
                                                                         (int)pl.rows_per_slab, pl.nslab);
@@ -1049,7 +1058,7 @@ extern "C" int mednet_upcat_groupnorm_split_fwd(const mednet_upcat_gn_split_fwd_
     const int64_t Sp = part == 0 ? S : S / 8;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
       gn_partial_kernel<T, VV><<<grid, block, smem, stream>>>((const T*)src, part == 0 ? pa : pb, Sp, Cp, pl.ncol,
                                                               pl.rows_per_slab, pl.nslab);
     });
@@ -1118,7 +1127,7 @@ extern "C" int mednet_upcat_groupnorm_split_bwd(const mednet_upcat_gn_split_bwd_
     const int64_t Sp = part == 0 ? S : S / 8;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      size_t smem = (size_t)pl.ncol_t * pl.R * 2 * VV * sizeof(float);
+      size_t smem = (size_t)pl.ncol_t * pl.R * RED_CHUNK * sizeof(float);
       gn_bwd_partial_kernel<T, VV><<<grid, block, smem, stream>>>(
           (const T*)(part == 0 ? p->skip : p->low), (const T*)nullptr, (const T*)(part == 0 ? p->dy_skip : p->dy_low),
           part == 0 ? pa : pb, Sp, Cp, pl.ncol, pl.rows_per_slab, pl.nslab, MEDNET_ACT_NONE, 0.f);
