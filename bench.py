@@ -595,14 +595,15 @@ def main():
         if elapsed > 8.0 or (elapsed > 1.5 and len(recent) == 3 and max(recent) < 1.02 * best):
             break
     step({k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}).item()
-    if rank == 0 and not os.environ.get("MEDNET_BENCH_NOSAMPLER"):
+    sampling = rank == 0 and not os.environ.get("MEDNET_BENCH_NOSAMPLER")
+    if sampling:
         sampler.start()
     ops.conv_events = None if os.environ.get("MEDNET_BENCH_NOEVENTS") else []   # per-launch CUDA events (see ops.k_conv3)
     launches0 = ops.launch_count
     ms = timed(lambda: step(batch_dev), args.steps)
     launches = ops.launch_count - launches0
     conv_events, ops.conv_events = ops.conv_events or [], None
-    clocks = sampler.stop() if (rank == 0 and sampler.running) else None
+    clocks = sampler.stop() if sampling else None
 
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}

@@ -105,3 +105,34 @@ def test_task_modules_construct_with_reference_hparams():
     ds = SyntheticSegmentationDataset(2, (8, 8, 8), num_classes=2, num_heatmaps=3)
     item = ds[0]
     assert item["data"].shape == (1, 8, 8, 8) and item["label"].shape == (4, 8, 8, 8) and item["label"].dtype == torch.uint8
+
+
+def test_fused_adam_state_dict_is_torch_adams_format_and_round_trips():
+    """FusedAdam.state_dict / load_state_dict (what Trainer.fit restores on resume_from_checkpoint, the reference's
+    examples/train_seg.py:122-131 through pytorch-lightning): torch.optim.Adam's own layout, one step count for the
+    bucket, a single parameter group."""
+    import pytest
+    import torch
+    from mednet_b200.optim import FusedAdam
+    ps = [torch.nn.Parameter(torch.randn(3, 2)), torch.nn.Parameter(torch.randn(4))]
+    opt = FusedAdam(ps, lr=2e-3, async_wgrad=False)
+    assert opt.state_dict()["state"] == {}                      # nothing stepped yet, like torch
+    opt._materialize()
+    opt._step = 7
+    opt._m.copy_(torch.arange(10.0))
+    opt._v.copy_(torch.arange(10.0) * 2)
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["lr"] == 2e-3 and sd["param_groups"][0]["params"] == [0, 1]
+    assert float(sd["state"][1]["step"]) == 7.0 and tuple(sd["state"][0]["exp_avg"].shape) == (3, 2)
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(4))])
+    ref.load_state_dict(sd)                                      # stock Adam accepts it
+    assert torch.equal(ref.state_dict()["state"][1]["exp_avg_sq"], torch.arange(6.0, 10.0) * 2)
+    opt2 = FusedAdam([torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(4))], async_wgrad=False)
+    opt2.load_state_dict(ref.state_dict())                       # and what stock Adam saved loads back
+    assert opt2._step == 7 and torch.equal(opt2._m, torch.arange(10.0)) and opt2.param_groups[0]["lr"] == 2e-3
+    with pytest.raises(NotImplementedError):
+        FusedAdam([{"params": ps[:1]}, {"params": ps[1:]}])
+    bad = ref.state_dict()
+    bad["state"][0]["step"] = torch.tensor(3.0)
+    with pytest.raises(ValueError, match="one step count"):
+        opt2.load_state_dict(bad)

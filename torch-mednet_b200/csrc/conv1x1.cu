@@ -42,6 +42,51 @@ __global__ void conv1_fwd_kernel(const T* __restrict__ x, const float* __restric
 }
 
 
+// One voxel per thread: the thread issues ALL 16-byte loads of its channel row first (CIN / 8 of them in flight), takes the
+// CO_T x CIN weights from shared memory (every lane reads the same address: broadcast) and writes CO_T NCDHW values that are
+// contiguous across the warp.  No shuffles, no staging tile, no block barrier per 256 voxels; a warp's row loads hit
+// each 128-byte line once per instruction and L1 serves the other seven.  bf16, CIN in {32, 64, 128}.
+template <int CIN, int CO_T>
+__global__ void __launch_bounds__(256) conv1_fwd_row_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            int64_t total, int64_t S, int Cout) {
+  __shared__ float ws[CO_T * CIN];
+  __shared__ float bs[CO_T];
+  for (int co0 = 0; co0 < Cout; co0 += CO_T) {
+    const int nco = min(CO_T, Cout - co0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < CO_T * CIN; i += blockDim.x) ws[i] = (i / CIN) < nco ? w[(co0 + i / CIN) * CIN + i % CIN] : 0.f;
+    if (threadIdx.x < CO_T) bs[threadIdx.x] = threadIdx.x < nco ? bias[co0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+      asm volatile("" ::: "memory");      // keep the weight reads inside the loop (hoisted, they cost CO_T * CIN registers)
+      uint4 raw[CIN / 8];
+      const uint4* row = reinterpret_cast<const uint4*>(x + r * CIN);
+#pragma unroll
+      for (int i = 0; i < CIN / 8; ++i) raw[i] = row[i];
+      float acc[CO_T];
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) acc[j] = bs[j];
+#pragma unroll
+      for (int i = 0; i < CIN / 8; ++i) {
+        float xv[8];
+        cvt_raw<bf16, 8>(raw[i], xv);
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + j * CIN + i * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + j * CIN + i * 8 + 4);
+          acc[j] = fmaf(xv[0], w0.x, fmaf(xv[1], w0.y, fmaf(xv[2], w0.z, fmaf(xv[3], w0.w, acc[j]))));
+          acc[j] = fmaf(xv[4], w1.x, fmaf(xv[5], w1.y, fmaf(xv[6], w1.z, fmaf(xv[7], w1.w, acc[j]))));
+        }
+      }
+      const int64_t n = r / S, sidx = r - n * S;
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+        if (j < nco) y[(n * Cout + co0 + j) * S + sidx] = acc[j];
+    }
+  }
+}
+
 // Coalesced forward for power-of-two Cin / V <= 32 (16-byte vectors): `ncol` adjacent lanes share one voxel row
 // (one fully used 16 B x ncol line per row), partial dot products are combined with warp shuffles, the block's
 // 256 voxels x CO_T results are staged in shared memory and written as contiguous NCDHW runs.
@@ -401,6 +446,19 @@ extern "C" int mednet_conv1x1_fwd(const mednet_conv1_params* p, mednet_stream_t 
   MEDNET_REQUIRE(smem <= 48 * 1024, MEDNET_EUNSUPPORTED);
   const int V = pick_vec(p->Cin, dtype_bytes(p->dtype));
   const int ncol = p->Cin / V;
+  if (p->dtype == MEDNET_BF16 && (p->Cin == 32 || p->Cin == 64 || p->Cin == 128) && (((uintptr_t)p->x) & 15) == 0) {
+    const int64_t total = p->N * p->S;
+    const int grid = grid_for(total, 256, 8);
+#define MEDNET_C1R(CI)                                                                                                   \
+    do {                                                                                                                 \
+      if (p->Cout <= 4) conv1_fwd_row_kernel<CI, 4><<<grid, 256, 0, stream>>>((const bf16*)p->x, p->w, p->bias, p->y, total, p->S, p->Cout); \
+      else conv1_fwd_row_kernel<CI, 8><<<grid, 256, 0, stream>>>((const bf16*)p->x, p->w, p->bias, p->y, total, p->S, p->Cout);              \
+    } while (0)
+    if (p->Cin == 32) MEDNET_C1R(32); else if (p->Cin == 64) MEDNET_C1R(64); else MEDNET_C1R(128);
+#undef MEDNET_C1R
+    MEDNET_LAUNCH_CHECK();
+    return MEDNET_OK;
+  }
   if (V * dtype_bytes(p->dtype) == 16 && ncol <= 32 && (ncol & (ncol - 1)) == 0) {
     const int64_t total = p->N * p->S;
     const int grid = grid_for(ceil_div64(total, 256) * 256, 256, 8);
