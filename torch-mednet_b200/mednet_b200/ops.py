@@ -6,6 +6,8 @@ Activations are NDHWC-contiguous tensors of shape (N, D, H, W, C) in the compute
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _abi
@@ -887,7 +889,7 @@ class UpcatGroupNormFn(torch.autograd.Function):
 # conv3(skip, W[:, :Cs]) + upconv(low, W[:, Cs:]) where the second term runs on the COARSE grid with 8 summed taps per output
 # parity class instead of 27 fine taps -- 2/3 of the decoder's input channels cost 3.4x fewer MMAs in fprop, dgrad and wgrad,
 # and the (Cs + Cl)-channel full-resolution tensor and its gradient are never written.
-UPCONV = __import__("os").environ.get("MEDNET_UPCONV", "1") != "0"
+UPCONV = os.environ.get("MEDNET_UPCONV", "1") != "0"          # A/B switch: "0" = materialised-concat path of round 1
 
 
 def upconv_supported(skip, low, weight):
