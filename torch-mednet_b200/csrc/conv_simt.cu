@@ -248,8 +248,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     const int b = (int)((i / 27) % Cb);
     const int a = (int)(i / (27 * (int64_t)Cb));
     const int64_t src = ((int64_t)a * 27 + tap) * Cb + b;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + src];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // interleaved partial sums: independent loads in flight, fixed order
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+      s0 += partial[(int64_t)z * total + src];
+      s1 += partial[(int64_t)(z + 1) * total + src];
+      s2 += partial[(int64_t)(z + 2) * total + src];
+      s3 += partial[(int64_t)(z + 3) * total + src];
+    }
+    for (; z < splits; ++z) s0 += partial[(int64_t)z * total + src];
+    const float s = (s0 + s1) + (s2 + s3);
     dw[i] = accumulate ? dw[i] + s : s;
   }
 }
@@ -338,30 +346,30 @@ __global__ void pack_weights_convt_kernel(const float* __restrict__ src, T* __re
 template <typename T>
 __global__ void pack_weights_upconv_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cin, int Cout, int dgrad) {
   const int Nout = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
-  const int64_t total = (int64_t)8 * 27 * Nout * K;
+  // only the 2x2x2 window of each class is enumerated (8 of 27 taps): taps outside it are never loaded by the kernel
+  // (tap mask) and are not written
+  const int64_t total = (int64_t)8 * 8 * Nout * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
     const int nout = (int)((i / K) % Nout);
-    const int tap = (int)((i / ((int64_t)K * Nout)) % 27);
-    const int cls = (int)(i / ((int64_t)K * Nout * 27));
-    const int kk[3] = {tap / 9, (tap / 3) % 3, tap % 3}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
-    // per axis: the set of fine taps (as indices 0..2) that map to coarse offset c for this parity; empty = tap unused
-    int lo[3], hi[3];
-    bool on = true;
+    const int t8 = (int)((i / ((int64_t)K * Nout)) % 8);
+    const int cls = (int)(i / ((int64_t)K * Nout * 8));
+    const int bit[3] = {t8 >> 2, (t8 >> 1) & 1, t8 & 1}, par[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+    // per axis: coarse offset c = bit - 1 + par (par 0: -1, 0;  par 1: 0, +1), the fine taps (indices 0..2) that map to
+    // it, and the window tap index it is stored under
+    int lo[3], hi[3], kk[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const int c = dgrad ? 1 - kk[a] : kk[a] - 1;
+      const int c = bit[a] - 1 + par[a];
       if (par[a] == 0) {
         if (c == -1) { lo[a] = 0; hi[a] = 0; }          // o = -1
-        else if (c == 0) { lo[a] = 1; hi[a] = 2; }       // o = 0, +1
-        else on = false;
+        else { lo[a] = 1; hi[a] = 2; }                   // o = 0, +1
       } else {
         if (c == 0) { lo[a] = 0; hi[a] = 1; }            // o = -1, 0
-        else if (c == 1) { lo[a] = 2; hi[a] = 2; }       // o = +1
-        else on = false;
+        else { lo[a] = 2; hi[a] = 2; }                   // o = +1
       }
+      kk[a] = dgrad ? 1 - c : c + 1;
     }
-    if (!on) continue;           // taps outside the class's 2x2x2 window are never loaded by the kernel (tap mask): not written
     float v = 0.f;
     {
       const int ci = dgrad ? nout : k, co = dgrad ? k : nout;
@@ -370,7 +378,8 @@ __global__ void pack_weights_upconv_kernel(const float* __restrict__ src, T* __r
         for (int oh = lo[1]; oh <= hi[1]; ++oh)
           for (int ow = lo[2]; ow <= hi[2]; ++ow) v += w[(od * 3 + oh) * 3 + ow];
     }
-    dst[i] = from_f32<T>(v);
+    const int tap = (kk[0] * 3 + kk[1]) * 3 + kk[2];
+    dst[(((int64_t)cls * 27 + tap) * Nout + nout) * K + k] = from_f32<T>(v);
   }
 }
 
@@ -1043,7 +1052,7 @@ extern "C" int mednet_conv3d_pack_weights(const mednet_wpack_params* p, mednet_s
   if (p->layout == MEDNET_WPACK_TC_UPCONV_F || p->layout == MEDNET_WPACK_TC_UPCONV_B) {
     MEDNET_REQUIRE(!p->transposed, MEDNET_EINVAL);
     const int dg = p->layout == MEDNET_WPACK_TC_UPCONV_B ? 1 : 0;
-    const int64_t tot = (int64_t)8 * 27 * p->Cin * p->Cout;
+    const int64_t tot = (int64_t)8 * 8 * p->Cin * p->Cout;
     if (p->dtype == MEDNET_F32)
       pack_weights_upconv_kernel<float><<<grid_for(tot, 256), 256, 0, stream>>>((const float*)p->w_oidhw, (float*)p->w_packed,
                                                                                p->Cin, p->Cout, dg);

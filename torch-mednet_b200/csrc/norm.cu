@@ -372,8 +372,10 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ dgb, float* __rest
   }
 }
 
-template <typename T, int V>
-__global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+// ACT = false: no activation after the norm and no residual branch (every GroupNorm of the 'gcr' blocks): x and dy are the
+// only streams, four rows of each in flight per thread (the ACT = true body keeps two: it also holds y)
+template <typename T, int V, bool ACT>
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                     const float* __restrict__ coef, T* __restrict__ dx,
                                     T* __restrict__ dresidual, int64_t S, int C, int ncol,
                                     int64_t rows_per_slab, int act, float act_param, int in_act, float in_act_param) {
@@ -392,7 +394,7 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
   }
   const int64_t base = (int64_t)n * S * C + (int64_t)col * V;
   const int64_t R = blockDim.y;
-  constexpr int U2 = USTD / 2;
+  constexpr int U2 = ACT ? USTD / 2 : USTD;
   for (int64_t r = r0 + threadIdx.y; r < r1; r += U2 * R) {
     typename RawVec<sizeof(T) * V>::type rx[U2], rg[U2], ry[U2];
 #pragma unroll
@@ -400,7 +402,7 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
       if (r + u * R < r1) {
         rx[u] = load_raw<T, V>(x + base + (r + u * R) * C);
         rg[u] = load_raw<T, V>(dy + base + (r + u * R) * C);
-        if (act != MEDNET_ACT_NONE) ry[u] = load_raw<T, V>(y + base + (r + u * R) * C);
+        if (ACT && act != MEDNET_ACT_NONE) ry[u] = load_raw<T, V>(y + base + (r + u * R) * C);
       }
 #pragma unroll
     for (int u = 0; u < U2; ++u)
@@ -408,13 +410,13 @@ __global__ void gn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
         float xv[V], gv[V];
         cvt_raw<T, V>(rx[u], xv);
         cvt_raw<T, V>(rg[u], gv);
-        if (act != MEDNET_ACT_NONE) {
+        if (ACT && act != MEDNET_ACT_NONE) {
           float yv[V];
           cvt_raw<T, V>(ry[u], yv);
 #pragma unroll
           for (int i = 0; i < V; ++i) gv[i] *= act_grad_from_out(yv[i], act, act_param);
         }
-        if (dresidual != nullptr) store_vec<T, V>(dresidual + base + (r + u * R) * C, gv);
+        if (ACT && dresidual != nullptr) store_vec<T, V>(dresidual + base + (r + u * R) * C, gv);
         if (in_act != MEDNET_ACT_NONE) {            // deferred derivative of the activation that produced x
 #pragma unroll
           for (int i = 0; i < V; ++i)
@@ -835,12 +837,21 @@ extern "C" int mednet_groupnorm_bwd(const mednet_gn_bwd_params* p, void* workspa
   gn_bwd_param_kernel<<<ceil_div(p->C, 128), 128, 0, stream>>>(dgb, p->dgamma, p->dbeta, (int)p->N, p->C,
                                                                p->accumulate);
   MEDNET_LAUNCH_CHECK();
-  MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-    gn_bwd_apply_kernel<T, VV><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy, coef,
-                                                           (T*)p->dx, (T*)p->dresidual, p->S, p->C, pl.ncol,
-                                                           pl.rows_per_slab, p->act, p->act_param, p->in_act,
-                                                           p->in_act_param);
-  });
+  if (p->act == MEDNET_ACT_NONE && p->dresidual == nullptr) {
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      gn_bwd_apply_kernel<T, VV, false><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy, coef,
+                                                                    (T*)p->dx, (T*)nullptr, p->S, p->C, pl.ncol,
+                                                                    pl.rows_per_slab, p->act, p->act_param, p->in_act,
+                                                                    p->in_act_param);
+    });
+  } else {
+    MEDNET_DISPATCH_TV(p->dtype, pl.V, {
+      gn_bwd_apply_kernel<T, VV, true><<<grid, block, 0, stream>>>((const T*)p->x, (const T*)p->y, (const T*)p->dy, coef,
+                                                                   (T*)p->dx, (T*)p->dresidual, p->S, p->C, pl.ncol,
+                                                                   pl.rows_per_slab, p->act, p->act_param, p->in_act,
+                                                                   p->in_act_param);
+    });
+  }
   MEDNET_LAUNCH_CHECK();
   return MEDNET_OK;
 }
@@ -1145,7 +1156,7 @@ extern "C" int mednet_upcat_groupnorm_split_bwd(const mednet_upcat_gn_split_bwd_
     const int64_t Sp = part == 0 ? S : S / 8;
     dim3 grid(pl.nslab, (unsigned)p->N, pl.coltiles), block(pl.ncol_t, pl.R);
     MEDNET_DISPATCH_TV(p->dtype, pl.V, {
-      gn_bwd_apply_kernel<T, VV><<<grid, block, 0, stream>>>(
+      gn_bwd_apply_kernel<T, VV, false><<<grid, block, 0, stream>>>(
           (const T*)(part == 0 ? p->skip : p->low), (const T*)nullptr, (const T*)(part == 0 ? p->dy_skip : p->dy_low),
           part == 0 ? coef_a : coef_b, (T*)(part == 0 ? p->dskip : p->dlow), (T*)nullptr, Sp, Cp, pl.ncol, pl.rows_per_slab,
           MEDNET_ACT_NONE, 0.f, part == 0 ? p->skip_act : p->low_act, part == 0 ? p->skip_act_param : p->low_act_param);

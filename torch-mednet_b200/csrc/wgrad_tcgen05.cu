@@ -401,12 +401,25 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     const int wt = ((tile - (s1 ? seg1_tile : 0)) * s_chunks + cs / CS) * 2 + role;
     const int nk = s1 ? ksplit1 : ksplit, nw = s1 ? worktypes1 : worktypes;
     const float* src = partial + (s1 ? seg1_offset : 0) + ((size_t)wt * 128 + row) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
-    float acc = 0.f;
-    for (int k = 0; k < nk; ++k) acc += src[(size_t)k * nw * 128 * PART_COLS];
-    if (shared) {                              // the other role's share: work type + 1, slot 0
-      const float* src2 = src + (size_t)128 * PART_COLS - (size_t)gl * NCOLS;
-      for (int k = 0; k < nk; ++k) acc += src2[(size_t)k * nw * 128 * PART_COLS];
-    }
+    // four interleaved partial sums: the up-to-148 split partials are independent loads, a single running sum would
+    // serialise their latencies (the reduce launches were latency-bound: 37 of them cost 1.5 ms per step); the order is
+    // still fixed, hence deterministic
+    const size_t kst = (size_t)nw * 128 * PART_COLS;
+    auto sum_splits = [&](const float* s0) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 3 < nk; k += 4) {
+        a0 += s0[(size_t)k * kst];
+        a1 += s0[(size_t)(k + 1) * kst];
+        a2 += s0[(size_t)(k + 2) * kst];
+        a3 += s0[(size_t)(k + 3) * kst];
+      }
+      for (; k < nk; ++k) a0 += s0[(size_t)k * kst];
+      return (a0 + a1) + (a2 + a3);
+    };
+    float acc = sum_splits(src);
+    if (shared)                                // the other role's share: work type + 1, slot 0
+      acc += sum_splits(src + (size_t)128 * PART_COLS - (size_t)gl * NCOLS);
     // destination: dense (Ca, Cb, 27), or a channel range of a wider / transposed gradient tensor (mednet_wgrad_params)
     const int64_t o = dw_ld == 0 ? i
                                  : (dw_transposed ? ((int64_t)ci * dw_ld + dw_c0 + co) * 27 + tap
