@@ -242,6 +242,9 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.nvml = pynvml
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            # first use of the two queries of _loop here, outside any timed region (driver-side lazy setup)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
         except Exception:
             self.nvml = None
             try:
@@ -503,6 +506,8 @@ def main():
     ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     ap.add_argument("--kd-merge", type=int, default=1, help="tcgen05 conv: kd-merged wide-N MMAs (A/B switch)")
     ap.add_argument("--wgrad-dual", type=int, default=1, help="tcgen05 wgrad: second MMA-issuing thread (A/B switch)")
+    ap.add_argument("--wgrad-class-merge", type=int, default=1,
+                    help="tcgen05 wgrad parity-class passes: all tap groups in one role, needed kw windows only (A/B switch)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if wl.get("sampler"):
@@ -532,6 +537,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"dual_issue", args.dual_issue), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"kd_merge", args.kd_merge), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_dual_issue", args.wgrad_dual), "tcgen05_set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_class_merge", args.wgrad_class_merge), "tcgen05_set_option")
     hp = hparams_for(wl)
     if wl["arch"] == "residual":
         cls = LandmarkNet if wl["heatmaps"] else SegmentationNet

@@ -158,7 +158,8 @@ def test_wgrad_tcgen05_is_deterministic():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("cin,cout,shape", [(32, 16, (4, 16, 8)), (64, 32, (3, 9, 11)), (128, 64, (2, 5, 6)), (16, 16, (5, 4, 3))])
+@pytest.mark.parametrize("cin,cout,shape", [(32, 16, (4, 16, 8)), (64, 32, (3, 9, 11)), (128, 64, (2, 5, 6)), (16, 16, (5, 4, 3)),
+                                            (16, 32, (3, 4, 5))])
 def test_conv_transpose_tcgen05_exact_on_integer_data(cin, cout, shape):
     """ConvTranspose3d(k3, s2, p1, op1) + bias + skip sum on the tensor cores (8 parity classes of 1/2/4/8 taps;
     dgrad through a stride-2 TMA map) -- small-integer operands make every product and fp32 sum exact, so forward and

@@ -107,6 +107,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
   const int dh_code = ((d & 1) << 2) | ((h & 1) << 1);
   const int64_t lbase = (int64_t)line * W * C + cv * V;
   const int64_t pbase = (((int64_t)n * Do + od) * Ho + oh) * (int64_t)Wo * C + cv * V;
+#pragma unroll 2                                     // two voxels' loads in flight per thread
   for (int w = threadIdx.y; w < W; w += blockDim.y) {
     float g[V];
 #pragma unroll

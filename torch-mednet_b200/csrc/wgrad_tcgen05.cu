@@ -34,6 +34,7 @@ int g_pair_planes = 1;        // mednet_tcgen05_set_option("wgrad_pair_planes", 
 int g_d_fastest = 1;          // mednet_tcgen05_set_option("wgrad_d_fastest", 0|1)
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
 int g_dual = 1;               // mednet_tcgen05_set_option("wgrad_dual_issue", 0|1)
+int g_class_merge = 1;        // mednet_tcgen05_set_option("wgrad_class_merge", 0|1): parity-class passes in one role, needed kw windows only
 int g_profile = 0;            // mednet_tcgen05_set_option("wgrad_profile", 0|1): wait-cycle counters, see wgrad_tc_kernel<PROF>
 
 constexpr int WG_THREADS = 224;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue, warp 6: second MMA issuer
@@ -56,10 +57,13 @@ struct WgArgs {
   // parity (cls >> 2, cls >> 1 & 1, cls & 1); one launch per parity class, only the (kd, kh) groups in gmask are needed
   int u_scale, s_scale, cls;
   uint32_t gmask;
-  // Balanced tap-group table (parity-class passes of the conv over an upsampled input: 4 of the 9 (kd, kh) groups are
-  // needed; with the fixed 0..4 / 4..8 role ranges one role would compute 3.5 of them and the other 0.5): slot s of role r
-  // holds group tab[r][s] (-1 = unused), no shared group.  use_tab = 0: the fixed ranges + gmask.
-  int use_tab;
+  // Tap-group table of the parity-class passes (transposed conv, conv over an upsampled input): at most 4 of the 9
+  // (kd, kh) groups are needed, so ONE role holds them all (nroles = 1): slot s holds group tab[0][s] (-1 = unused).  A
+  // staged brick (110 KB at TD = 2) then feeds 4 MMAs per K step; split 2 + 2 over two roles every CTA pulled 61 B/clk
+  // through L2 for 2 MMAs per K step and the class passes ran at 59 % of the MMA rate (ncu launch list r02g: 350 us for
+  // 207 us of MMAs at 128x64 channels).  use_tab = 0: the fixed 0..4 / 4..8 ranges of the two roles.
+  // Only the kw windows a class needs are chained: ncols = 32 x their count, kw0 = the first one.
+  int use_tab, nroles, ncols, kw0;
   signed char tab[2][5];
   // second MMA-issuing thread (warp 6).  One thread sustains one tcgen05.mma per ~55-64 clk, the N = 96 MMA needs 56 clk of
   // shared-memory operand reads: two issuers, each owning a disjoint range of the CTA's tap-group accumulators, move the
@@ -118,11 +122,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   // (other S chunk, other U tile, other tap-group role) are launched together and walk the same brick range at the same
   // pace, so a brick is fetched from HBM once and re-read from L2 (ncu, 64x128@64^3: 3.6 GB of DRAM reads for 0.8 GB of
   // operands with the split index fastest).
-  const int worktypes = p.u_tiles * p.s_chunks * 2;
+  const int worktypes = p.u_tiles * p.s_chunks * p.nroles;
   int wt = p.wt_fastest ? blockIdx.x % worktypes : blockIdx.x / p.ksplit;
   const int ks = p.wt_fastest ? blockIdx.x / worktypes : blockIdx.x % p.ksplit;
   const int wt0 = wt;          // partial buffer layout [ks][work type] whatever the launch order
-  const int role = wt & 1; wt >>= 1;
+  const int role = p.nroles == 2 ? (wt & 1) : 0; wt /= p.nroles;
   const int sc = wt % p.s_chunks;
   const int ut = wt / p.s_chunks + p.ut_base;
   // PAIRED-PLANE mode for a U tile with <= 64 real channels (64-channel layers; the 64-channel tail of a 192-channel
@@ -228,14 +232,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
     // ===================== MMA issuer(s) =====================
     const int issuer = warp == 1 ? 0 : 1;
     if ((issuer == 0 || p.dual) && tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_16(128, NCOLS, 1, 1, 1, 1);
+      const uint32_t idesc = tc::make_idesc_16(128, p.ncols, 1, 1, 1, 1);
       // per-group window offset inside the halo, in descriptor units (16 bytes)
       uint32_t goff[GROUPS0];
 #pragma unroll
       for (int g = 0; g < GROUPS0; ++g) {
         const int gg = p.use_tab ? (g < ngroups ? p.tab[role][g] : p.tab[role][0]) : g0 + (g < ngroups ? g : 0);
         const int gd = paired ? 1 + role : gg / 3, gh = paired ? gg : gg - gd * 3;
-        goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W) * (2 * CS)) >> 4;
+        goff[g] = (uint32_t)(((gd * HL_H + gh) * HL_W + p.kw0) * (2 * CS)) >> 4;
       }
       const uint32_t s_base = tc::smem_u32(smem);
       // A: MN-major, 128-byte rows, atoms u_atom_bytes apart (paired mode: the same channels one 16 KB d-plane further),
@@ -274,7 +278,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         if (p.dual) {
           // each issuer owns a disjoint range of the brick's tap groups (their accumulators are disjoint TMEM columns)
           if (paired) { if (issuer == 0) WG_BRICK(0, 2); else WG_BRICK(2, 3); }
+          else if (p.use_tab && ngroups == 4) { if (issuer == 0) WG_BRICK(0, 2); else WG_BRICK(2, 4); }
           else if (p.use_tab && ngroups == 2) { if (issuer == 0) WG_BRICK(0, 1); else WG_BRICK(1, 2); }
+          else if (p.use_tab && ngroups == 1) { if (issuer == 0) WG_BRICK(0, 1); }
           else if (base_mask == 0x1fu) {
             if (shared_mine) { if (issuer == 0) WG_BRICK(0, 3); else WG_BRICK(3, 5); }
             else if (role == 0) { if (issuer == 0) WG_BRICK(0, 2); else WG_BRICK(2, 4); }
@@ -294,14 +300,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
           }
         } else if (paired) {
           WG_BRICK(0, 3);
+        } else if (p.use_tab && ngroups == 4) {
+          WG_BRICK(0, 4);
         } else if (p.use_tab && ngroups == 2) {
           WG_BRICK(0, 2);
+        } else if (p.use_tab && ngroups == 1) {
+          WG_BRICK(0, 1);
         } else if (base_mask == 0x1fu) {
           if (shared_mine) WG_BRICK(0, 5);
           else if (role == 0) WG_BRICK(0, 4);
           else WG_BRICK(1, 5);
         } else {
-          // transposed-conv parity classes: only the tap groups of gmask (at most 4 of 9), rare and small launches
+          // any other group subset (gmask with the fixed ranges): predicated, not used by the shipped plans
           const uint32_t act = shared_mine ? base_mask : (base_mask & ~shared_bit);
           for (int dz = 0; dz < p.TD; ++dz) {
             uint32_t a_lo = a_st + (uint32_t)dz * a_dz16, b_lo = b_st + (uint32_t)dz * b_dz16;
@@ -353,7 +363,7 @@ struct WgTab { int use; signed char where[9]; };     // where[group] = role * 8 
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
                                        int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset,
-                                       int upconv, WgTab tab, int dw_ld, int dw_c0, int dw_transposed) {
+                                       int upconv, WgTab tab, int nroles, int kw0, int dw_ld, int dw_c0, int dw_transposed) {
   // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
   // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
@@ -398,9 +408,9 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
     }
     const int tile = cu >> 7;
     const bool s1 = tile >= seg1_tile;
-    const int wt = ((tile - (s1 ? seg1_tile : 0)) * s_chunks + cs / CS) * 2 + role;
+    const int wt = ((tile - (s1 ? seg1_tile : 0)) * s_chunks + cs / CS) * nroles + role;
     const int nk = s1 ? ksplit1 : ksplit, nw = s1 ? worktypes1 : worktypes;
-    const float* src = partial + (s1 ? seg1_offset : 0) + ((size_t)wt * 128 + row) * PART_COLS + gl * NCOLS + kw * CS + (cs % CS);
+    const float* src = partial + (s1 ? seg1_offset : 0) + ((size_t)wt * 128 + row) * PART_COLS + gl * NCOLS + (kw - kw0) * CS + (cs % CS);
     // four interleaved partial sums: the up-to-148 split partials are independent loads, a single running sum would
     // serialise their latencies (the reduce launches were latency-bound: 37 of them cost 1.5 ms per step); the order is
     // still fixed, hence deterministic
@@ -457,6 +467,8 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   a.u_scale = (convt && pl.u_is_x) ? 2 : 1;                   // "u_is_x": U is operand b
   a.s_scale = (convt && !pl.u_is_x) ? 2 : 1;
   a.cls = 0; a.gmask = 0x1ffu; a.use_tab = 0; a.dual = g_dual;
+  a.nroles = (convt && g_class_merge) ? 1 : 2;                                   // parity-class passes: all (<= 4) tap groups in one role
+  a.ncols = NCOLS; a.kw0 = 0;
   for (int r = 0; r < 2; ++r)
     for (int i = 0; i < 5; ++i) a.tab[r][i] = -1;
   a.pair_ok = (!convt && g_pair_planes) ? 1 : 0;
@@ -472,7 +484,7 @@ bool plan_wgrad(const mednet_wgrad_params* q, WgPlan* out) {
   auto add_seg = [&](int ut_base, int u_tiles, bool paired) {
     WgSeg& sg = pl.seg[pl.nseg++];
     sg.ut_base = ut_base; sg.u_tiles = u_tiles;
-    const int worktypes = u_tiles * a.s_chunks * 2;
+    const int worktypes = u_tiles * a.s_chunks * a.nroles;
     const int64_t bricks = (int64_t)a.N * (a.tiles_d + (paired ? 1 : 0)) * a.tiles_h * a.tiles_w;
     // one CTA is resident per SM (224 KB of shared memory): AT MOST two full waves, never a third, nearly empty one
     // (rounding the split factor up gave e.g. 312 CTAs = 148 + 148 + 16 for 384x128 channels: 30 % of the launch idle)
@@ -506,6 +518,7 @@ void tc_wgrad_set_pair_planes(int v) { g_pair_planes = v ? 1 : 0; }
 void tc_wgrad_set_d_fastest(int v) { g_d_fastest = v ? 1 : 0; }
 void tc_wgrad_set_profile(int v) { g_profile = v ? 1 : 0; }
 void tc_wgrad_set_dual(int v) { g_dual = v ? 1 : 0; }
+void tc_wgrad_set_class_merge(int v) { g_class_merge = v ? 1 : 0; }
 size_t tc_wgrad_profile_offset(const mednet_wgrad_params* q) {
   WgPlan pl;
   if (!plan_wgrad(q, &pl)) return 0;
@@ -610,9 +623,9 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
   for (int i = 0; i < 9; ++i) wtab.where[i] = 0;
   auto reduce = [&](int cls) -> int {
     wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-        (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * 2,
-        q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * 2, (int64_t)s1.offset_floats,
-        upconv ? 1 : 0, wtab, q->dw_ld, q->dw_c0, q->dw_transposed);
+        (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * a.nroles,
+        q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * a.nroles, (int64_t)s1.offset_floats,
+        upconv ? 1 : 0, wtab, a.nroles, a.kw0, q->dw_ld, q->dw_c0, q->dw_transposed);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   };
@@ -637,18 +650,30 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
           gm |= 1u << (gd * 3 + gh);
         }
       a.cls = cls; a.gmask = gm;
-      if (upconv) {      // the 4 needed groups, two per role
+      {                  // the (1, 2 or 4) needed groups, all in role 0 (A/B switch off: two per role)
         a.use_tab = 1; wtab.use = 1;
+        const int per_role = a.nroles == 1 ? 4 : 2;
         int cnt = 0;
         for (int r = 0; r < 2; ++r)
           for (int i = 0; i < 5; ++i) a.tab[r][i] = -1;
         for (int g = 0; g < 9; ++g)
           if ((gm >> g) & 1u) {
-            const int r = cnt / 2, sl = cnt % 2;
+            const int r = cnt / per_role, sl = cnt % per_role;
             a.tab[r][sl] = (signed char)g;
             wtab.where[g] = (signed char)(r * 8 + sl);
             ++cnt;
           }
+      }
+      if (g_class_merge) {          // kw windows of this class (same rule as kd, kh above), mirrored when U is the strided operand
+        int lo = 3, hi = -1;
+        for (int kw = 0; kw < 3; ++kw) {
+          if (upconv ? ((cls & 1) ? kw > 1 : kw < 1) : (kw == 2 || (kw == 0 && !(cls & 1)))) continue;
+          const int gw = pl.u_is_x ? 2 - kw : kw;
+          if (gw < lo) lo = gw;
+          if (gw > hi) hi = gw;
+        }
+        a.kw0 = lo;
+        a.ncols = (hi - lo + 1) * CS;
       }
       int r = launch_all();
       if (r != MEDNET_OK) return r;
