@@ -506,6 +506,8 @@ def main():
     ap.add_argument("--dual-issue", type=int, default=1, help="tcgen05 conv: second MMA-issuing thread (A/B switch)")
     ap.add_argument("--kd-merge", type=int, default=1, help="tcgen05 conv: kd-merged wide-N MMAs (A/B switch)")
     ap.add_argument("--wgrad-dual", type=int, default=1, help="tcgen05 wgrad: second MMA-issuing thread (A/B switch)")
+    ap.add_argument("--class-merge", type=int, default=1,
+                    help="tcgen05 fprop/dgrad of the upsample-conv parity classes: kd-merged MMAs, TD + 1 planes (A/B switch)")
     ap.add_argument("--wgrad-class-merge", type=int, default=1,
                     help="tcgen05 wgrad parity-class passes: all tap groups in one role, needed kw windows only (A/B switch)")
     args = ap.parse_args()
@@ -538,6 +540,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"kd_merge", args.kd_merge), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_dual_issue", args.wgrad_dual), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_class_merge", args.wgrad_class_merge), "tcgen05_set_option")
+    check(lib().mednet_tcgen05_set_option(b"class_merge", args.class_merge), "tcgen05_set_option")
     hp = hparams_for(wl)
     if wl["arch"] == "residual":
         cls = LandmarkNet if wl["heatmaps"] else SegmentationNet
@@ -551,13 +554,26 @@ def main():
     batch_host = synthetic_batch(wl, 1000 + rank, dev, pin=True)
     h2d = sum(v.numel() * v.element_size() for v in batch_host.values())
 
+    inflight = []
+
     def step(batch):
+        # The host is kept at most ONE step ahead of the device (it waits for the end of step i-1 before it enqueues step
+        # i+1; a full step of queued work never lets the GPU starve).  Unbounded, the host ran 4-5 steps ahead in a 10-step
+        # region but at most 3 in the warm-up, and the first timed region was intermittently 4-6 % slower than the
+        # identical region measured after it (81.99 / 79.78 ms against 77.7 / 75.2 ms end-to-end in the same process,
+        # profiles/r02/r02n_*, r02o_*; the per-launch conv timings were FASTER in those regions, i.e. the device was
+        # waiting, not slow).  The end-to-end region, which reads the loss every step, never showed it.
+        if len(inflight) > 1:
+            inflight.pop(0).synchronize()
         out = model.training_step(batch, 0)
         out["loss"].backward()
         if reducer is not None:
             opt.grad_scale = reducer.finish()
         opt.step()
         opt.zero_grad()
+        ev = torch.cuda.Event()
+        ev.record()
+        inflight.append(ev)
         return out["loss"]
 
     def barrier():
@@ -601,6 +617,9 @@ def main():
         if elapsed > 8.0 or (elapsed > 1.5 and len(recent) == 3 and max(recent) < 1.02 * best):
             break
     step({k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}).item()
+    for _ in range(args.steps):              # dress rehearsal of the timed region (same queueing pattern, untimed)
+        step(batch_dev)
+    torch.cuda.synchronize()
     sampling = rank == 0 and not os.environ.get("MEDNET_BENCH_NOSAMPLER")
     if sampling:
         sampler.start()
@@ -639,6 +658,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "per_gpu_batch": wl["batch"], "patch": wl["edge"],
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (activations are GBs per step)",
+                       "host_run_ahead": "at most one step",
                        "conv_impl": args.conv_impl, "tcgen05_variants": {str(k): v for k, v in ops.tcgen05_variants.items()
                                                                            if k != "report"}},
             "clocks": clocks,

@@ -172,10 +172,14 @@ def layerwise_report(net, x, y, weight, f_maps):
         want = r16(want) if rounded else want
         rows.append((layer, what, relerr(got, want), cosine(got, want)))
 
-    def param_rows(prefix, mod):
+    def param_rows(prefix, mod, exact=None):
         for pname, p in mod.named_parameters():
             got, want = p.grad.float(), o["grads"][prefix + pname]
-            if want.numel() < 8 and pname == "groupnorm.weight" and hasattr(mod, "conv"):
+            if exact is not None and pname in exact:
+                rows.append((prefix, "d" + pname + " (vs unrounded dxn, f64)", relerr(got, exact[pname]), 1.0))
+                rows.append((prefix, "d" + pname + " (bf16-storage oracle vs the same f64 value: its own rounding noise, not gated)",
+                             relerr(want, exact[pname]), 1.0))
+            elif want.numel() < 8 and pname == "groupnorm.weight" and hasattr(mod, "conv"):
                 # A handful of numbers that are ~0 by construction: the next GroupNorm makes the loss invariant to the
                 # scale of this layer's (ReLU) output, so dgamma = sum_v dxn * xhat = sum W (.) dW cancels to ~1e-5 of its
                 # terms.  Its error is measured against the size of those terms (Cauchy-Schwarz bound ||W|| ||dW||).
@@ -229,6 +233,20 @@ def layerwise_report(net, x, y, weight, f_maps):
                 if not first:
                     gx = tg(xin)
                     add(prefix, "dx", ncdhw(xi.grad), gx * (xin > 0) if in_act else gx)
+                else:
+                    # One-channel GroupNorm of the image: dbeta = sum_v dxn[v] is ONE number, a sum of 2 M signed terms.  The
+                    # bf16-storage oracle rounds dxn to bf16 before summing (noise ~2^-9 ||dxn||_2 / sqrt 3: 1e-4 .. 1e-2 of
+                    # the sum, depending on how much of it cancels in the state at hand -- 1.5e-4, 1.4e-3 and 6.9e-3 were
+                    # seen on three trained states); the product never materialises dxn, so it has no such
+                    # rounding and is compared with the unrounded evaluation of the same formula in float64.
+                    g64 = (tg(yout) * (yout > 0)).double()
+                    wq = r16(mod.conv.weight.detach().float()).double()
+                    dxn = torch.nn.grad.conv3d_input(list(xin.shape), wq, g64, padding=1)
+                    first_exact = {"groupnorm.bias": dxn.sum(dim=(0, 2, 3, 4)).float()}
+                    del g64, dxn
+                    param_rows(prefix, mod, first_exact)
+                    after_pool = False
+                    continue
             param_rows(prefix, mod)
             after_pool = False
         elif kind == "final":

@@ -76,6 +76,8 @@ def test_layerwise_teacher_forced_parity_cfg3_size(state):
             assert rel == 0.0, (layer, what, rel)
         elif "abs diff" in what:
             assert rel < 1e-5, (layer, what, rel)
+        elif "not gated" in what:                       # the comparator's own noise, reported next to the gated row
+            continue
         else:
             assert rel <= 5e-3 and c >= 0.9999, (layer, what, rel, c)
 

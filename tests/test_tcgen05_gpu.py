@@ -193,7 +193,8 @@ def _upconv_ref(xl, w):
     return F.conv3d(F.interpolate(xl, scale_factor=2, mode="nearest"), w, None, padding=1)
 
 
-@pytest.mark.parametrize("cl,cout,shape", [(32, 64, (3, 16, 8)), (128, 64, (2, 8, 8)), (64, 32, (5, 9, 7))])
+@pytest.mark.parametrize("cl,cout,shape", [(32, 64, (3, 16, 8)), (128, 64, (2, 8, 8)), (64, 32, (5, 9, 7)),
+                                           (128, 64, (4, 8, 8)), (64, 256, (5, 8, 8))])
 def test_upsample_conv_tcgen05_exact_on_integer_data(cl, cout, shape):
     """MEDNET_GATHER_UPCONV_F / _B and the UPCONV_B weight gradient: conv3(nearest_up2(x)) evaluated on the coarse grid
     (8 summed taps per output parity class) against F.interpolate + F.conv3d on small-integer data -- every product and

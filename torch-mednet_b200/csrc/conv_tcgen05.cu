@@ -48,6 +48,8 @@ static int g_dense_halo[3] = {0, 0, 0};        // 0: halo rows padded to a 16-vo
 static int g_base_offset_mode[3] = {1, 1, 1};  // 0: base_offset = 0; 1: (addr >> 7) & 7; 2: (addr / row_bytes) & 7
 static int g_dual_issue = 1;                  // mednet_tcgen05_set_option("dual_issue", 0|1)
 static int g_kd_merge = 1;                    // mednet_tcgen05_set_option("kd_merge", 0|1): kd-merged wide-N MMAs (see TcConv::mt)
+static int g_class_merge = 1;                 // mednet_tcgen05_set_option("class_merge", 0|1): the same for the parity classes of the
+                                              // upsample conv (see TcConv::cmerge)
 static inline int rb_class(int rb) { return rb == 128 ? 0 : rb == 64 ? 1 : 2; }
 
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
@@ -69,6 +71,13 @@ struct TcConv {
   // 96 clk), and one issuing thread suffices (one instruction per >= 64 clk of math).  mt = taps per MMA (1 = off).
   int mt;
   int b_tile;                  // bytes of one [Ntile x chunk] weight tile (a B stage holds 3 of them in kd-merged mode)
+  // Class-merged mode (parity classes of the conv over a nearest-upsampled input, MEDNET_GATHER_UPCONV_*): every class has
+  // exactly 2 x 2 x 2 taps, kd in {kd_lo, kd_lo + 1}.  mt = 2: halo plane kd_lo + j feeds accumulators j (tap kd_lo) and
+  // j - 1 (tap kd_lo + 1) with ONE MMA of N = 2 * Ntile; only the TD + 1 planes a class needs are staged (slot j = plane
+  // kd_lo + j) and only its four (kh,kw) windows are visited.  The plain class path (one MMA per tap and plane, all TD + 2
+  // planes, planes released per kd phase) ran at 57 % of its shared-memory bound: with a single halo set 4 of the 6 planes
+  // of the next chunk could not be requested before the current chunk's last MMA.
+  int cmerge, nplanes;
   int a_stages;                // halo sets in shared memory.  The kd-merged order needs every plane until the last (kh,kw)
                                // window, so it works on 32-channel chunks with TWO halo sets: the next chunk streams in
                                // under the current chunk's MMAs (with one set the tensor pipe idles for a halo load per chunk)
@@ -242,7 +251,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
-  uint8_t* b_base = a_base + (size_t)p.a_stages * (p.TD + 2) * p.plane_bytes;
+  uint8_t* b_base = a_base + (size_t)p.a_stages * p.nplanes * p.plane_bytes;
   uint64_t* bars = (uint64_t*)(b_base + (size_t)p.BS * p.b_bytes);
   uint64_t* a_full = bars;                       // [a_stages][MAX_PLANES]
   uint64_t* a_empty = bars + 2 * MAX_PLANES;
@@ -253,7 +262,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nplanes = p.TD + 2;
+  const int nplanes = p.nplanes;
 
   if (threadIdx.x == 0) {
     const uint32_t nissue = p.dual ? 2u : 1u;         // every issuer commits to the barriers the MMAs release
@@ -297,7 +306,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const TileCoord tc_ = decode_tile(p, t);
         for (int ci = 0; ci < p.ncls_in; ++ci) {
           const int s = p.in_scale;
-          const int cw = s * (tc_.w0 - 1) + (ci & 1), ch = s * (tc_.h0 - 1) + ((ci >> 1) & 1), cd0 = s * (tc_.d0 - 1) + (ci >> 2);
+          // class-merged mode: slot j holds plane kd_lo + j of the class (the other plane of the TD + 2 halo is never read)
+          const int kd_lo = (p.cmerge && !(p.tapmask[p.ncls_out > 1 ? tc_.cls : ci] & 0x1ffu)) ? 1 : 0;
+          const int cw = s * (tc_.w0 - 1) + (ci & 1), ch = s * (tc_.h0 - 1) + ((ci >> 1) & 1),
+                    cd0 = s * (tc_.d0 - 1 + kd_lo) + (ci >> 2);
           for (int c = 0; c < p.nchunks; ++c, ++ait) {
             const uint32_t ast = ait % (uint32_t)p.a_stages, aph = (ait / (uint32_t)p.a_stages) & 1u;
             uint64_t* full = a_full + ast * MAX_PLANES;
@@ -330,6 +342,22 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int wcls = p.ncls_out > 1 ? tc_.cls : ci;          // weight set / tap mask of this (tile, input class)
           const uint32_t mask = p.tapmask[wcls];
           for (int c = 0; c < p.nchunks; ++c) {
+            if (p.cmerge) {
+              // class-merged mode: one stage = the two kd tiles of one of the class's four (kh,kw) windows
+              const int kd_lo = (mask & 0x1ffu) ? 0 : 1;
+              const uint32_t gm = (mask >> (kd_lo * 9)) & 0x1ffu;
+              for (int g = 0; g < 9; ++g) {
+                if (!((gm >> g) & 1u)) continue;
+                const uint32_t st = bit % (uint32_t)p.BS, ph = (bit / (uint32_t)p.BS) & 1u;
+                ++bit;
+                pwait<PROF>(&b_empty[st], ph ^ 1u, w_empty);
+                tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)(2 * p.b_tile));
+                for (int k2 = 0; k2 < 2; ++k2)
+                  tc::tma_load_2d(b_base + (size_t)st * p.b_bytes + (size_t)k2 * p.b_tile, &map_w, &b_full[st], c * KC,
+                                  (wcls * 27 + (kd_lo + k2) * 9 + g) * p.Nout + tc_.n0);
+              }
+              continue;
+            }
             if (p.mt > 1) {
               // kd-merged mode: one stage = the three kd tiles of one (kh,kw), adjacent in shared memory
               for (int g = 0; g < 9; ++g) {
@@ -405,17 +433,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint64_t* a_full_s = a_full + ast * MAX_PLANES;
             uint64_t* a_empty_s = a_empty + ast * MAX_PLANES;
             const uint32_t a_lo_s = a_lo0 + ast * (uint32_t)nplanes * plane16;
-            if (p.mt > 1) {
-              // ---- kd-merged issue order: (kh,kw) outer, halo plane inner; see TcConv::mt.  Every accumulator column is
-              // zero when its tile starts (the epilogue clears what it has read), so all MMAs accumulate.  Planes 0 / 1
-              // reach 1 / 2 d-planes, the interior planes 3, planes TD / TD+1 again 2 / 1:
-              //   plane pl, taps kd_lo..kd_hi -> accumulators dz = pl-kd_lo .. pl-kd_hi = columns (TD-1-dz)*Ntile ascending
-              for (int g = 0; g < 9; ++g) {
-                pwait<PROF>(&b_full[bst], bph, w_b);
-                tc::tc_fence_after();
-                const uint32_t b0 = b_lo0 + bst * b16, b1 = b0 + tile16, b2 = b1 + tile16;
-                uint32_t a = a_lo_s + tapoff9(g, tap_h, tap_w);
-                const bool first_g = g == 0, last_g = g == 8;
 #define KDM_PLANE(PL, DCOL, BLO, IDESC)                                                          \
                 {                                                                                \
                   if (first_g) { pwait<PROF>(&a_full_s[PL], aph, w_a); tc::tc_fence_after(); }   \
@@ -434,12 +451,44 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   if (last_g) tc::umma_commit(&a_empty_s[PL]);                                   \
                   a += plane16;                                                                  \
                 }
+            if (p.cmerge) {
+              // ---- class-merged issue order (see TcConv::cmerge): the class's four (kh,kw) windows outer, its TD + 1 halo
+              // planes inner.  Slot j = plane kd_lo + j: tap kd_lo -> accumulator j, tap kd_lo + 1 -> accumulator j - 1, i.e.
+              // columns (TD-1-j)*Ntile and the next Ntile (decreasing-d layout); all MMAs accumulate (zeroed accumulators)
+              const uint32_t kd_lo = (mask & 0x1ffu) ? 0u : 1u;
+              const uint32_t gm = (mask >> (kd_lo * 9u)) & 0x1ffu;
+              const int g_first = __ffs((int)gm) - 1, g_last = 31 - __clz((int)gm);
+              for (int g = g_first; g <= g_last; ++g) {
+                if (!((gm >> g) & 1u)) continue;
+                pwait<PROF>(&b_full[bst], bph, w_b);
+                tc::tc_fence_after();
+                const uint32_t b0 = b_lo0 + bst * b16, b1 = b0 + tile16;
+                uint32_t a = a_lo_s + tapoff9(g, tap_h, tap_w);
+                const bool first_g = g == g_first, last_g = g == g_last;
+                KDM_PLANE(0, dcol_top, b0, id1)
+                for (int j = 1; j < p.TD; ++j) KDM_PLANE(j, dcol_top - (uint32_t)j * ntile, b0, id2)
+                KDM_PLANE(p.TD, 0u, b1, id1)
+                tc::umma_commit(&b_empty[bst]);
+                if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
+              }
+              continue;
+            }
+            if (p.mt > 1) {
+              // ---- kd-merged issue order: (kh,kw) outer, halo plane inner; see TcConv::mt.  Every accumulator column is
+              // zero when its tile starts (the epilogue clears what it has read), so all MMAs accumulate.  Planes 0 / 1
+              // reach 1 / 2 d-planes, the interior planes 3, planes TD / TD+1 again 2 / 1:
+              //   plane pl, taps kd_lo..kd_hi -> accumulators dz = pl-kd_lo .. pl-kd_hi = columns (TD-1-dz)*Ntile ascending
+              for (int g = 0; g < 9; ++g) {
+                pwait<PROF>(&b_full[bst], bph, w_b);
+                tc::tc_fence_after();
+                const uint32_t b0 = b_lo0 + bst * b16, b1 = b0 + tile16, b2 = b1 + tile16;
+                uint32_t a = a_lo_s + tapoff9(g, tap_h, tap_w);
+                const bool first_g = g == 0, last_g = g == 8;
                 KDM_PLANE(0, dcol_top, b0, id1)
                 KDM_PLANE(1, dcol_top - ntile, b0, id2)
                 for (int pl = 2; pl < p.TD; ++pl) KDM_PLANE(pl, dcol_top - (uint32_t)pl * ntile, b0, id3)
                 KDM_PLANE(p.TD, 0u, b1, id2)
                 KDM_PLANE(p.TD + 1, 0u, b2, id1)
-#undef KDM_PLANE
                 tc::umma_commit(&b_empty[bst]);
                 if (++bst == (uint32_t)p.BS) { bst = 0; bph ^= 1u; }
               }
@@ -493,6 +542,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tc::umma_commit(&acc_full[as]);
       }
+#undef KDM_PLANE
       (void)bit;
       if (PROF && issuer == 0) { prof[0] = clock64() - t_begin; prof[1] = w_a; prof[2] = w_b; prof[3] = w_acc; }
     }
@@ -570,14 +620,22 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   }
   p.RB = pick_row_bytes(q->K);
   p.Ntile = pick_ntile(q->Nout, q->K);
+  if (up && g_class_merge && p.Ntile > 128 && q->Nout % 128 == 0) p.Ntile = 128;     // class-merged MMAs: N = 2 * Ntile <= 256
   if (p.RB == 0 || p.Ntile == 0 || (q->Nout % 16) != 0) return false;
   // more planes per brick = fewer halo re-reads and weight-tile loads per voxel; TMEM holds TD * Ntile columns per stage
   p.TD = (p.Ntile <= 64 && p.D >= 4) ? 4 : (p.D >= 2 ? 2 : 1);
+  p.cmerge = (up && g_class_merge && p.D >= 2 && 2 * p.Ntile <= 256 && ((p.Ntile * p.RB) % 1024) == 0) ? 1 : 0;
+  // class-merged 128-channel tiles: four planes per brick with ONE accumulator stage (4 x 128 = all 512 TMEM columns) --
+  // with TD = 2 a staged weight pair (32 KB) feeds 12 MMAs and the launch is bound by L2 (48 B/clk per SM); the epilogue it
+  // no longer overlaps is ~5 % of a tile that runs 8 classes (dgrad) or >= 4 chunks (fprop)
+  if (p.cmerge && p.Ntile == 128 && p.D >= 4) p.TD = 4;
+  p.nplanes = p.cmerge ? p.TD + 1 : p.TD + 2;
   // kd-merged MMAs: plain conv, up to 128-channel output tiles, 32-channel chunks (64-byte rows) so that two halo sets fit
   p.mt = 1;
   p.a_stages = 1;
   if (g_kd_merge && !tf && !tb && p.TD >= 2 && ((p.Ntile * p.RB) % 1024) == 0)
     p.mt = 3 * p.Ntile <= 256 ? 3 : ((2 * p.Ntile <= 256 && p.TD == 2) ? 2 : 1);
+  if (p.cmerge) p.mt = 2;
   p.nchunks = q->K / (p.RB / 2);
   const int rc = rb_class(p.RB);
   if (!g_enabled[rc] || g_base_offset_mode[rc] != 0) return false;   // the kernel issues base_offset = 0 descriptors
@@ -586,10 +644,10 @@ static bool plan_tc(const mednet_conv3d_params* q, TcConv* out) {
   p.bo_mode = g_base_offset_mode[rc];
   p.plane_bytes = (int)align_up((size_t)HALO_H * p.pitch * p.RB, 1024);
   p.b_tile = p.Ntile * p.RB;                     // a multiple of 1024 in kd-merged mode (Ntile % 16 == 0, 64-byte rows)
-  p.b_bytes = p.mt > 1 ? 3 * p.b_tile : (int)align_up((size_t)p.b_tile, 1024);
+  p.b_bytes = p.cmerge ? 2 * p.b_tile : (p.mt > 1 ? 3 * p.b_tile : (int)align_up((size_t)p.b_tile, 1024));
   const int budget = 227 * 1024 - 1024 - 1024;   // alignment slack + barrier block
-  if (p.mt > 1 && 2 * (p.TD + 2) * p.plane_bytes + 3 * p.b_bytes <= budget) p.a_stages = 2;
-  int bs = (budget - p.a_stages * (p.TD + 2) * p.plane_bytes) / p.b_bytes;
+  if (p.mt > 1 && 2 * p.nplanes * p.plane_bytes + 3 * p.b_bytes <= budget) p.a_stages = 2;
+  int bs = (budget - p.a_stages * p.nplanes * p.plane_bytes) / p.b_bytes;
   if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
   if (p.mt > 1 && bs > 4) bs = 4;
   if (bs < 2) return false;
@@ -657,7 +715,7 @@ int tc_fprop(const mednet_conv3d_params* q, void* workspace, size_t workspace_by
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MEDNET_EUNSUPPORTED;
   }
-  const size_t smem = 1024 + (size_t)p.a_stages * (p.TD + 2) * p.plane_bytes + (size_t)p.BS * p.b_bytes + 1024;
+  const size_t smem = 1024 + (size_t)p.a_stages * p.nplanes * p.plane_bytes + (size_t)p.BS * p.b_bytes + 1024;
   static std::mutex mu;
   static size_t configured = 0;
   {
@@ -767,6 +825,7 @@ extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
   MEDNET_REQUIRE(name != nullptr, MEDNET_EINVAL);
   if (strcmp(name, "dual_issue") == 0) { g_dual_issue = value ? 1 : 0; return MEDNET_OK; }
   if (strcmp(name, "kd_merge") == 0) { g_kd_merge = value ? 1 : 0; return MEDNET_OK; }
+  if (strcmp(name, "class_merge") == 0) { g_class_merge = value ? 1 : 0; return MEDNET_OK; }
   if (strcmp(name, "conv_profile") == 0) { g_conv_profile = value ? 1 : 0; return MEDNET_OK; }
   if (strcmp(name, "ntile_max") == 0) { g_ntile_max = value >= 256 ? 256 : 128; return MEDNET_OK; }
   if (strcmp(name, "wgrad_wt_fastest") == 0) { tc_wgrad_set_wt_fastest(value); return MEDNET_OK; }
