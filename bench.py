@@ -508,6 +508,8 @@ def main():
     ap.add_argument("--wgrad-dual", type=int, default=1, help="tcgen05 wgrad: second MMA-issuing thread (A/B switch)")
     ap.add_argument("--class-merge", type=int, default=1,
                     help="tcgen05 fprop/dgrad of the upsample-conv parity classes: kd-merged MMAs, TD + 1 planes (A/B switch)")
+    ap.add_argument("--wgrad-reduce-s-fastest", type=int, default=0,
+                    help="tcgen05 wgrad split reduction: coalesced thread order (A/B switch)")
     ap.add_argument("--wgrad-class-merge", type=int, default=1,
                     help="tcgen05 wgrad parity-class passes: all tap groups in one role, needed kw windows only (A/B switch)")
     args = ap.parse_args()
@@ -541,6 +543,7 @@ def main():
     check(lib().mednet_tcgen05_set_option(b"wgrad_dual_issue", args.wgrad_dual), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"wgrad_class_merge", args.wgrad_class_merge), "tcgen05_set_option")
     check(lib().mednet_tcgen05_set_option(b"class_merge", args.class_merge), "tcgen05_set_option")
+    check(lib().mednet_tcgen05_set_option(b"wgrad_reduce_s_fastest", args.wgrad_reduce_s_fastest), "tcgen05_set_option")
     hp = hparams_for(wl)
     if wl["arch"] == "residual":
         cls = LandmarkNet if wl["heatmaps"] else SegmentationNet

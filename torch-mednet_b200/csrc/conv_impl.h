@@ -29,6 +29,7 @@ void tc_wgrad_set_d_fastest(int v);
 void tc_wgrad_set_profile(int v);
 void tc_wgrad_set_dual(int v);
 void tc_wgrad_set_class_merge(int v);
+void tc_wgrad_set_reduce_s_fastest(int v);
 size_t tc_wgrad_workspace_bytes(const mednet_wgrad_params* p);
 int tc_wgrad(const mednet_wgrad_params* p, void* workspace, cudaStream_t st);
 }  // namespace mednet

@@ -834,6 +834,7 @@ extern "C" int mednet_tcgen05_set_option(const char* name, int value) {
   if (strcmp(name, "wgrad_profile") == 0) { tc_wgrad_set_profile(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_dual_issue") == 0) { tc_wgrad_set_dual(value); return MEDNET_OK; }
   if (strcmp(name, "wgrad_class_merge") == 0) { tc_wgrad_set_class_merge(value); return MEDNET_OK; }
+  if (strcmp(name, "wgrad_reduce_s_fastest") == 0) { tc_wgrad_set_reduce_s_fastest(value); return MEDNET_OK; }
   if (strcmp(name, "first_layer_mma") == 0) { in1_mma_set_enabled(value); return MEDNET_OK; }
   return MEDNET_EINVAL;
 }

@@ -35,6 +35,7 @@ int g_d_fastest = 1;          // mednet_tcgen05_set_option("wgrad_d_fastest", 0|
 int g_wt_fastest = 1;         // mednet_tcgen05_set_option("wgrad_wt_fastest", 0|1)
 int g_dual = 1;               // mednet_tcgen05_set_option("wgrad_dual_issue", 0|1)
 int g_class_merge = 1;        // mednet_tcgen05_set_option("wgrad_class_merge", 0|1): parity-class passes in one role, needed kw windows only
+int g_reduce_s_fastest = 0;   // mednet_tcgen05_set_option("wgrad_reduce_s_fastest", 0|1): thread order of the split reduction (A/B switch)
 int g_profile = 0;            // mednet_tcgen05_set_option("wgrad_profile", 0|1): wait-cycle counters, see wgrad_tc_kernel<PROF>
 
 constexpr int WG_THREADS = 224;          // warp 0: TMA, warp 1: MMA issuer (+TMEM alloc), warps 2..5: epilogue, warp 6: second MMA issuer
@@ -363,14 +364,32 @@ struct WgTab { int use; signed char where[9]; };     // where[group] = role * 8 
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin,
                                        int u_is_x, int s_chunks, int ksplit, int worktypes, int accumulate, int cls,
                                        int CU, int pair_ok, int seg1_tile, int ksplit1, int worktypes1, int64_t seg1_offset,
-                                       int upconv, WgTab tab, int nroles, int kw0, int dw_ld, int dw_c0, int dw_transposed) {
+                                       int upconv, WgTab tab, int nroles, int kw0, int dw_ld, int dw_c0, int dw_transposed,
+                                       int s_fastest) {
   // partial buffer: segment 0 = U tiles [0, seg1_tile) as [ksplit][worktypes][128][PART_COLS]; segment 1 (the paired
   // tail tile, if any) starts at seg1_offset floats with its own split factor
   const int64_t total = (int64_t)Cout * Cin * 27;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % 27);
-    const int ci = (int)((i / 27) % Cin);
-    const int co = (int)(i / (27 * (int64_t)Cin));
+  // Thread order.  Default: the output order (tap fastest) -- the read-modify-write of dw is contiguous, every lane's load
+  // of a split is its own 32-byte sector (the neighbouring sectors are used by the next warps, out of L2).  s_fastest: S
+  // channel fastest, then tap, then U channel -- a warp reads one 128-byte line per split and scatters its results at a
+  // 27-float stride.  Measured on one box (cfg-3, profiles/r02/r02s_bench_cfg3_reduce_order_*.json): 73.3 ms/step with
+  // the output order against 74.9 with s_fastest, so the coalesced reads do not pay for the scattered read-modify-write;
+  // kept as an A/B switch.  The 37 reduce launches cost 2.0 ms per step (profiles/r02/kernels_r02q.txt).
+  const int CSn = u_is_x ? Cout : Cin;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int tap, co, ci;
+    if (s_fastest) {
+      const int cs_f = (int)(j % CSn);
+      tap = (int)((j / CSn) % 27);
+      const int cu_f = (int)(j / (27 * (int64_t)CSn));
+      co = u_is_x ? cs_f : cu_f;
+      ci = u_is_x ? cu_f : cs_f;
+    } else {                                                       // output order (tap fastest): the A/B baseline
+      tap = (int)(j % 27);
+      ci = (int)((j / 27) % Cin);
+      co = (int)(j / (27 * (int64_t)Cin));
+    }
+    const int64_t i = ((int64_t)co * Cin + ci) * 27 + tap;         // index in the dense (Cout, Cin, 27) gradient
     int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
     if (cls >= 0 && upconv) {
       // conv over the nearest-upsampled input: EVERY fine tap o receives a share from every dY parity class p, namely the
@@ -519,6 +538,7 @@ void tc_wgrad_set_d_fastest(int v) { g_d_fastest = v ? 1 : 0; }
 void tc_wgrad_set_profile(int v) { g_profile = v ? 1 : 0; }
 void tc_wgrad_set_dual(int v) { g_dual = v ? 1 : 0; }
 void tc_wgrad_set_class_merge(int v) { g_class_merge = v ? 1 : 0; }
+void tc_wgrad_set_reduce_s_fastest(int v) { g_reduce_s_fastest = v ? 1 : 0; }
 size_t tc_wgrad_profile_offset(const mednet_wgrad_params* q) {
   WgPlan pl;
   if (!plan_wgrad(q, &pl)) return 0;
@@ -625,7 +645,7 @@ int tc_wgrad(const mednet_wgrad_params* q, void* workspace, cudaStream_t st) {
     wgrad_tc_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(
         (const float*)workspace, q->dw, q->Ca, q->Cb, pl.u_is_x, a.s_chunks, s0.ksplit, s0.u_tiles * a.s_chunks * a.nroles,
         q->accumulate, cls, a.CU, a.pair_ok, seg1_tile, s1.ksplit, s1.u_tiles * a.s_chunks * a.nroles, (int64_t)s1.offset_floats,
-        upconv ? 1 : 0, wtab, a.nroles, a.kw0, q->dw_ld, q->dw_c0, q->dw_transposed);
+        upconv ? 1 : 0, wtab, a.nroles, a.kw0, q->dw_ld, q->dw_c0, q->dw_transposed, g_reduce_s_fastest);
     MEDNET_LAUNCH_CHECK();
     return MEDNET_OK;
   };
