@@ -544,8 +544,18 @@ int mednet_intensity_augment(const mednet_intensity_aug_params* p, void* workspa
  *   base_offset_mode: 0 -> descriptor base_offset 0; 1 -> (start >> 7) & 7; 2 -> (start / row_bytes) & 7.
  * ---------------------------------------------------------------------------------------------- */
 int mednet_tcgen05_configure(int row_bytes, int enabled, int dense_halo, int base_offset_mode);
-/* Tuning switches of the tensor-core conv (A/B measurements): "dual_issue" 0|1 = second MMA-issuing thread for
- * output tiles of <= 96 channels (default 1). */
+/* Tuning switches of the tensor-core kernels (A/B measurements; every default is the measured-faster setting):
+ *   "dual_issue" 0|1             second MMA-issuing thread for output tiles of <= 96 channels (1)
+ *   "kd_merge" 0|1               plain conv: the kd taps of one (kh,kw) window in ONE wide-N MMA (1)
+ *   "class_merge" 0|1            the same for the parity classes of MEDNET_GATHER_UPCONV_F/B (1)
+ *   "ntile_max" 128|256          widest output-channel tile (128)
+ *   "wgrad_dual_issue" 0|1       second MMA-issuing thread of the weight-gradient kernel (1)
+ *   "wgrad_class_merge" 0|1      parity-class wgrad passes: all tap groups in one role, needed kw windows only (1)
+ *   "wgrad_reduce_s_fastest" 0|1 thread order of the split reduction (0)
+ *   "wgrad_wt_fastest", "wgrad_pair_planes", "wgrad_d_fastest" 0|1   round-1 switches (1)
+ *   "first_layer_mma" 0|1        Cin = 1 forward / weight gradient on mma.sync (1)
+ *   "conv_profile", "wgrad_profile" 0|1   per-CTA wait-cycle counters written behind the workspace (0)
+ * Unknown names return MEDNET_EINVAL. */
 int mednet_tcgen05_set_option(const char* name, int value);
 int mednet_tcgen05_probe(const void* a_bf16 /* [rows][row_bytes/2] */, int32_t row_bytes, int32_t rows,
                          int32_t row_shift, int32_t sbo_bytes, int32_t base_offset_mode,
