@@ -9,11 +9,16 @@ One step = one pass of the hot path over one synthetic batch: forward -> loss ->
   value      whole-job voxels/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e        same metric through the public training_step API with HOST (pinned) batches: the H2D copy of
              every step's inputs and the D2H read of the loss are inside the timed region
-  roofline   dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs of its launches divided
-             by their summed CUDA-event durations, against the measured dense bf16 peak
-  cpu_baseline  the oracle port (plain PyTorch fp32, oracle/) timed on the host cores on a bounded sample
+  roofline   dominant kernel (tcgen05 implicit-GEMM conv): the FLOPs its launches execute divided by their
+             summed CUDA-event durations, against the measured sustained dense bf16 peak
+             (`reference_equivalent`: the same with the FLOPs of the reference's ops those launches replace)
+  cpu_baseline  the reference's own modules (oracle/_ref, kind "reference"; the oracle port when absent)
+             timed on the host cores on a bounded sample: batch 1 on the workload's own patch edge
+  clocks     SM clock / throttle reasons sampled through NVML during the timed region
 `--impl reference` times that CPU path alone with all host threads (the reference ships no GPU kernels of
 its own: every FLOP of it runs inside stock PyTorch).
+The host is kept at most one step ahead of the device and the timed region is rehearsed once, untimed
+(`config.host_run_ahead`; DESIGN.md section 6 "Measurement hygiene").
 """
 from __future__ import annotations
 
