@@ -136,3 +136,35 @@ def test_fused_adam_state_dict_is_torch_adams_format_and_round_trips():
     bad["state"][0]["step"] = torch.tensor(3.0)
     with pytest.raises(ValueError, match="one step count"):
         opt2.load_state_dict(bad)
+
+
+def test_load_from_checkpoint_reads_a_pl09_shaped_file(tmp_path):
+    """examples/predict.py:46-50 loads `SegmentationNet.load_from_checkpoint(path)` on files written by pytorch-lightning
+    0.9.  pytorch-lightning is absent here, so the file is assembled by hand with the keys PL 0.9's
+    `Trainer.dump_checkpoint` writes (epoch, global_step, pytorch-lightning_version, checkpoint_callback_*,
+    optimizer_states, lr_schedulers, state_dict, hparams_name, hyper_parameters): the loader must take the weights
+    and the hyper-parameters from it and ignore the rest."""
+    import argparse
+    import torch
+    hp = dict(in_channels=1, out_channels=2, fmaps=8, learning_rate=1e-3, num_workers=0, batch_size=2, loss="DICE",
+              loss_weight=[0.05, 1.0])
+    torch.manual_seed(3)
+    src = SegmentationNet(argparse.Namespace(**hp))
+    adam = torch.optim.Adam(src.parameters(), lr=1e-3)
+    ckpt = {"epoch": 4, "global_step": 120, "pytorch-lightning_version": "0.9.0",
+            "checkpoint_callback_best_model_score": torch.tensor(0.41), "checkpoint_callback_best_model_path": "epoch=3.ckpt",
+            "optimizer_states": [adam.state_dict()], "lr_schedulers": [],
+            "state_dict": {k: v.clone() for k, v in src.state_dict().items()},
+            "hparams_name": "hparams", "hyper_parameters": dict(hp)}
+    path = str(tmp_path / "epoch=4.ckpt")
+    torch.save(ckpt, path)
+    net = SegmentationNet.load_from_checkpoint(path)
+    assert vars(net.hparams) == hp
+    assert list(net.state_dict()) == list(src.state_dict())
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), src.state_dict().values()))
+    # the older layout of the same release line: the Namespace itself under 'hparams'
+    ckpt2 = dict(ckpt)
+    ckpt2.pop("hyper_parameters")
+    ckpt2["hparams"] = argparse.Namespace(**hp)
+    torch.save(ckpt2, path)
+    assert vars(SegmentationNet.load_from_checkpoint(path).hparams) == hp
